@@ -1,0 +1,721 @@
+// capi.cu — the C ABI of libalice_codec (declared in include/alice_codec.h).
+// Part 1 mirrors src/ffi.rs of the reference symbol for symbol; Part 2 are the extensions.
+// Every compute entry point runs on the CUDA device; there is no CPU fallback.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/alice_codec.h"
+#include "engine.h"
+#include "lifting.cuh"
+
+using namespace alice;
+
+struct Wavelet1D { int kind; };                       // wavelet.rs:47-50 (step list chosen by kind)
+struct FrameEncoder { uint8_t quality; uint8_t wavelet; };   // pipeline.rs:335-340
+struct EncodedChunk { Chunk c; };
+struct AliceBatch {
+    Engine *eng = nullptr;
+    uint8_t quality = 0, wavelet = 0;
+    std::vector<uint8_t *> stage_ptrs;
+};
+
+#define CU_CHECK_RC(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            set_error(kErrCuda, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+            return kErrCuda;                                                                \
+        }                                                                                   \
+    } while (0)
+
+namespace {
+// scoped device buffer
+struct DevBuf {
+    void *p = nullptr;
+    bool alloc(size_t bytes) {
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            set_error(kErrCuda, "device memory allocation failed");
+            return false;
+        }
+        return true;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+uint8_t *boxed_copy(const uint8_t *src, size_t len) {
+    // Rust's Box<[u8]> of length 0 is a dangling non-null pointer; we hand out a 1-byte block instead.
+    uint8_t *p = (uint8_t *)malloc(len ? len : 1);
+    if (p && len) memcpy(p, src, len);
+    return p;
+}
+
+int wavelet_nd(uint8_t wavelet, bool inverse, int32_t *data, uint64_t w, uint64_t h, uint64_t d, int ndim) {
+    if (!data) { set_error(kErrNull, "null data"); return kErrNull; }
+    if (wavelet > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return kErrBitstream; }
+    unsigned __int128 tot = (unsigned __int128)w * h * d;
+    if (tot > ((unsigned __int128)1 << 40)) { set_error(kErrOverflow, "volume too large"); return kErrOverflow; }
+    const size_t n = (size_t)tot;
+    if (n == 0) return kOk;
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a, b;
+    if (!a.alloc(n * 4) || !b.alloc(n * 4)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, data, n * 4, cudaMemcpyHostToDevice));
+    int32_t *A = a.as<int32_t>(), *B = b.as<int32_t>();
+    // wavelet.rs:392-438 / 441-484 (3-D), :292-340 (2-D), :133-176 (1-D)
+    if (!inverse) {
+        lift_axis(A, B, wavelet, false, 0, (long long)w, (long long)h, (long long)d, nullptr);
+        if (ndim >= 2) lift_axis(A, B, wavelet, false, 1, (long long)w, (long long)h, (long long)d, nullptr);
+        if (ndim >= 3) lift_axis(A, B, wavelet, false, 2, (long long)w, (long long)h, (long long)d, nullptr);
+    } else {
+        if (ndim >= 3) lift_axis(A, B, wavelet, true, 2, (long long)w, (long long)h, (long long)d, nullptr);
+        if (ndim >= 2) lift_axis(A, B, wavelet, true, 1, (long long)w, (long long)h, (long long)d, nullptr);
+        lift_axis(A, B, wavelet, true, 0, (long long)w, (long long)h, (long long)d, nullptr);
+    }
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(data, a.p, n * 4, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+// FrameEncoder::encode validation (pipeline.rs:384-427); returns kOk with empty=true for zero-area input
+int validate_encode(uint64_t rgb_len, uint32_t w, uint32_t h, uint32_t f, Dims &d, bool &empty) {
+    empty = false;
+    int rc = make_dims(w, h, f, d);
+    if (rc) return rc;
+    if (d.n_pixels == 0) {
+        if (rgb_len != 0) { set_error(kErrBufferSize, "buffer size mismatch: expected 0"); return kErrBufferSize; }
+        empty = true;
+        return kOk;
+    }
+    if (w == 0 || h == 0) { set_error(kErrDimensions, "invalid dimensions"); return kErrDimensions; }
+    unsigned __int128 e = (unsigned __int128)d.n_pixels * 3;
+    if (e > (unsigned __int128)UINT64_MAX) { set_error(kErrOverflow, "dimensions overflow usize"); return kErrOverflow; }
+    if (rgb_len != (uint64_t)e) { set_error(kErrBufferSize, "buffer size mismatch"); return kErrBufferSize; }
+    if (d.padded > 0xffffffffull) {
+        // num_symbols and the histogram counts are u32 in the .alc format (pipeline.rs:131-133)
+        set_error(kErrOverflow, "padded volume exceeds the u32 symbol count of the .alc format");
+        return kErrOverflow;
+    }
+    return kOk;
+}
+
+EncodedChunk *encode_impl(const FrameEncoder *enc, const uint8_t *rgb, uint64_t rgb_len, uint32_t w, uint32_t h,
+                          uint32_t f, int32_t *coeffs_out, uint8_t *symbols_out) {
+    set_error(0, "");
+    if (!enc || !rgb) { set_error(kErrNull, "null argument"); return nullptr; }
+    Dims d;
+    bool empty;
+    if (validate_encode(rgb_len, w, h, f, d, empty)) return nullptr;
+    EncodedChunk *out = new (std::nothrow) EncodedChunk();
+    if (!out) return nullptr;
+    out->c.width = w; out->c.height = h; out->c.frames = f;
+    out->c.wavelet = enc->wavelet;
+    if (empty) return out;  // three default headers, empty payload (pipeline.rs:391-412)
+    if (!cuda_ready()) { delete out; return nullptr; }
+    Engine *e = acquire_engine(d);
+    if (!e) { delete out; return nullptr; }
+    int rc = kOk;
+    DevBuf coef;
+    do {
+        uint8_t *stage = e->rgb_stage(0);
+        if (!stage) { rc = kErrCuda; break; }
+        if (cudaMemcpyAsync(stage, rgb, (size_t)rgb_len, cudaMemcpyHostToDevice, e->stream()) != cudaSuccess) {
+            set_error(kErrCuda, "H2D copy failed"); rc = kErrCuda; break;
+        }
+        if (coeffs_out && !coef.alloc((size_t)d.padded * 3 * 4)) { rc = kErrCuda; break; }
+        const uint8_t *ptrs[1] = {stage};
+        rc = e->encode_device(enc->quality, enc->wavelet, ptrs, 1, coef.as<int32_t>());
+        if (rc) break;
+        rc = e->fetch_chunk(0, out->c);
+        if (rc) break;
+        if (coeffs_out && cudaMemcpy(coeffs_out, coef.p, (size_t)d.padded * 3 * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error(kErrCuda, "D2H copy failed"); rc = kErrCuda; break;
+        }
+        if (symbols_out && cudaMemcpy(symbols_out, e->symbols_dev(0), (size_t)d.padded * 3, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error(kErrCuda, "D2H copy failed"); rc = kErrCuda; break;
+        }
+    } while (0);
+    release_engine(e);
+    if (rc) { delete out; return nullptr; }
+    return out;
+}
+
+uint8_t *decode_impl(const EncodedChunk *chunk, uint64_t *out_len, uint8_t *symbols_out) {
+    set_error(0, "");
+    if (!chunk || !out_len) { set_error(kErrNull, "null argument"); return nullptr; }
+    const Chunk &c = chunk->c;
+    Dims d;
+    if (make_dims(c.width, c.height, c.frames, d)) return nullptr;
+    if (d.n_pixels == 0) { *out_len = 0; return boxed_copy(nullptr, 0); }  // pipeline.rs:543-545
+    if (d.padded > 0xffffffffull) { set_error(kErrBitstream, "num_symbols != padded_pixels"); return nullptr; }
+    if (!cuda_ready()) return nullptr;
+    // cheap header validation first, so that malformed chunks fail without touching the device
+    {
+        size_t off = 0;
+        for (int k = 0; k < 3; k++) {
+            if ((uint64_t)c.ch[k].num_symbols != d.padded) { set_error(kErrBitstream, "num_symbols != padded_pixels"); return nullptr; }
+            if (off + c.ch[k].compressed_len > c.data.size()) { set_error(kErrBitstream, "compressed data overrun"); return nullptr; }
+            off += c.ch[k].compressed_len;
+        }
+    }
+    Engine *e = acquire_engine(d);
+    if (!e) return nullptr;
+    uint8_t *res = nullptr;
+    do {
+        uint8_t *stage = e->rgb_stage(0);
+        if (!stage) break;
+        const Chunk *cks[1] = {&c};
+        uint8_t *outs[1] = {stage};
+        if (e->decode_chunks(cks, 1, outs)) break;
+        const size_t len = (size_t)d.n_pixels * 3;
+        res = (uint8_t *)malloc(len);
+        if (!res) break;
+        if (cudaMemcpy(res, stage, len, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error(kErrCuda, "D2H copy failed"); free(res); res = nullptr; break;
+        }
+        if (symbols_out && cudaMemcpy(symbols_out, e->symbols_dev(0), (size_t)d.padded * 3, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error(kErrCuda, "D2H copy failed"); free(res); res = nullptr; break;
+        }
+        *out_len = len;
+    } while (0);
+    release_engine(e);
+    return res;
+}
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// =============================================================== Part 1: reference ABI
+Wavelet1D *alice_codec_wavelet1d_haar(void) { return new (std::nothrow) Wavelet1D{WT_HAAR}; }
+Wavelet1D *alice_codec_wavelet1d_cdf53(void) { return new (std::nothrow) Wavelet1D{WT_CDF53}; }
+Wavelet1D *alice_codec_wavelet1d_cdf97(void) { return new (std::nothrow) Wavelet1D{WT_CDF97}; }
+void alice_codec_wavelet1d_destroy(Wavelet1D *p) { delete p; }
+
+void alice_codec_wavelet1d_forward(const Wavelet1D *wv, int32_t *data, uint32_t len) {
+    if (!wv || !data || len < 2) return;  // ffi.rs:57
+    wavelet_nd((uint8_t)wv->kind, false, data, len, 1, 1, 1);
+}
+void alice_codec_wavelet1d_inverse(const Wavelet1D *wv, int32_t *data, uint32_t len) {
+    if (!wv || !data || len < 2) return;  // ffi.rs:78
+    wavelet_nd((uint8_t)wv->kind, true, data, len, 1, 1, 1);
+}
+
+FrameEncoder *alice_codec_encoder_create(uint8_t quality) { return new (std::nothrow) FrameEncoder{quality, WT_CDF53}; }
+void alice_codec_encoder_destroy(FrameEncoder *p) { delete p; }
+
+EncodedChunk *alice_codec_encode(const FrameEncoder *enc, const uint8_t *rgb, uint32_t rgb_len, uint32_t width,
+                                 uint32_t height, uint32_t frames) {
+    return encode_impl(enc, rgb, rgb_len, width, height, frames, nullptr, nullptr);
+}
+
+uint8_t *alice_codec_decode(const EncodedChunk *chunk, uint32_t *out_len) {
+    if (!chunk || !out_len) return nullptr;
+    uint64_t n = 0;
+    uint8_t *p = decode_impl(chunk, &n, nullptr);
+    if (p) *out_len = (uint32_t)n;  // `rgb.len() as u32`, ffi.rs:157
+    return p;
+}
+
+void alice_codec_chunk_destroy(EncodedChunk *p) { delete p; }
+
+uint8_t *alice_codec_chunk_to_bytes(const EncodedChunk *chunk, uint32_t *out_len) {
+    if (!chunk || !out_len) return nullptr;
+    std::vector<uint8_t> b = chunk->c.to_bytes();
+    *out_len = (uint32_t)b.size();
+    return boxed_copy(b.data(), b.size());
+}
+EncodedChunk *alice_codec_chunk_from_bytes(const uint8_t *data, uint32_t len) {
+    return alice_codec_chunk_from_bytes64(data, len);
+}
+uint32_t alice_codec_chunk_width(const EncodedChunk *c) { return c ? c->c.width : 0; }
+uint32_t alice_codec_chunk_height(const EncodedChunk *c) { return c ? c->c.height : 0; }
+uint32_t alice_codec_chunk_frames(const EncodedChunk *c) { return c ? c->c.frames : 0; }
+
+// metrics.rs:16-63 — a 10-line host-side f64 reduction used by callers for reporting; not on the codec path.
+double alice_codec_psnr(const uint8_t *a, const uint8_t *b, uint32_t len) {
+    if (!a || !b) return -1.0;
+    if (len == 0) return INFINITY;
+    double sum = 0.0;
+    for (uint32_t i = 0; i < len; i++) {
+        double diff = (double)a[i] - (double)b[i];
+        sum += diff * diff;
+    }
+    double mse = sum / (double)len;
+    if (mse == 0.0) return INFINITY;
+    return 10.0 * log10(255.0 * 255.0 / mse);
+}
+
+void alice_codec_data_free(uint8_t *ptr, uint32_t len) { if (ptr && len > 0) free(ptr); }
+void alice_codec_string_free(char *s) { free(s); }
+char *alice_codec_version(void) {
+    const char v[] = "0.1.2";  // CARGO_PKG_VERSION of the reference this library is ABI-compatible with
+    char *p = (char *)malloc(sizeof(v));
+    if (p) memcpy(p, v, sizeof(v));
+    return p;
+}
+
+// =============================================================== Part 2: extensions
+int32_t alice_codec_last_error(void) { return last_error_code(); }
+const char *alice_codec_last_error_message(void) { return last_error_msg(); }
+
+FrameEncoder *alice_codec_encoder_create_with_wavelet(uint8_t quality, uint8_t wavelet) {
+    if (wavelet > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return nullptr; }
+    return new (std::nothrow) FrameEncoder{quality, wavelet};
+}
+uint8_t alice_codec_chunk_wavelet(const EncodedChunk *c) { return c ? c->c.wavelet : 0; }
+uint64_t alice_codec_chunk_compressed_size(const EncodedChunk *c) { return c ? c->c.data.size() : 0; }
+int alice_codec_chunk_channel_header(const EncodedChunk *c, uint32_t channel, uint32_t *compressed_len,
+                                     int32_t *quant_step, int32_t *quant_dead_zone, uint32_t *num_symbols,
+                                     uint32_t *hist256) {
+    if (!c || channel > 2) { set_error(kErrNull, "null chunk or channel > 2"); return kErrNull; }
+    const ChannelHeader &h = c->c.ch[channel];
+    if (compressed_len) *compressed_len = h.compressed_len;
+    if (quant_step) *quant_step = h.quant_step;
+    if (quant_dead_zone) *quant_dead_zone = h.quant_dead_zone;
+    if (num_symbols) *num_symbols = h.num_symbols;
+    if (hist256) memcpy(hist256, h.histogram, sizeof(h.histogram));
+    return kOk;
+}
+uint8_t *alice_codec_chunk_to_bytes64(const EncodedChunk *chunk, uint64_t *out_len) {
+    if (!chunk || !out_len) return nullptr;
+    std::vector<uint8_t> b = chunk->c.to_bytes();
+    *out_len = b.size();
+    return boxed_copy(b.data(), b.size());
+}
+EncodedChunk *alice_codec_chunk_from_bytes64(const uint8_t *data, uint64_t len) {
+    set_error(0, "");
+    if (!data) { set_error(kErrNull, "null data"); return nullptr; }
+    EncodedChunk *c = new (std::nothrow) EncodedChunk();
+    if (!c) return nullptr;
+    if (Chunk::from_bytes(data, (size_t)len, c->c)) { delete c; return nullptr; }
+    return c;
+}
+void alice_codec_data_free64(uint8_t *ptr, uint64_t) { free(ptr); }
+
+int alice_codec_rgb_to_ycocg_r(const uint8_t *rgb, uint64_t rgb_len, int16_t *y, int16_t *co, int16_t *cg,
+                               uint64_t out_len) {
+    set_error(0, "");
+    if (rgb_len % 3 != 0) { set_error(kErrBufferSize, "rgb length not a multiple of 3"); return kErrBufferSize; }
+    const size_t n = (size_t)(rgb_len / 3);
+    if (out_len < n) { set_error(kErrBufferSize, "output smaller than pixel count"); return kErrBufferSize; }
+    if (n == 0) return kOk;
+    if (!rgb || !y || !co || !cg) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf in, o;
+    if (!in.alloc(n * 3) || !o.alloc(n * 6)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(in.p, rgb, n * 3, cudaMemcpyHostToDevice));
+    int16_t *dy = o.as<int16_t>();
+    rgb_to_ycocg(in.as<uint8_t>(), dy, dy + n, dy + 2 * n, n, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(y, dy, n * 2, cudaMemcpyDeviceToHost));
+    CU_CHECK_RC(cudaMemcpy(co, dy + n, n * 2, cudaMemcpyDeviceToHost));
+    CU_CHECK_RC(cudaMemcpy(cg, dy + 2 * n, n * 2, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+int alice_codec_ycocg_r_to_rgb(const int16_t *y, const int16_t *co, const int16_t *cg, uint64_t n64, uint8_t *rgb,
+                               uint64_t rgb_len) {
+    set_error(0, "");
+    const size_t n = (size_t)n64;
+    if (rgb_len < (uint64_t)n * 3) { set_error(kErrBufferSize, "rgb_out smaller than 3*n"); return kErrBufferSize; }
+    if (n == 0) return kOk;
+    if (!rgb || !y || !co || !cg) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf in, o;
+    if (!in.alloc(n * 6) || !o.alloc(n * 3)) return kErrCuda;
+    int16_t *dy = in.as<int16_t>();
+    CU_CHECK_RC(cudaMemcpy(dy, y, n * 2, cudaMemcpyHostToDevice));
+    CU_CHECK_RC(cudaMemcpy(dy + n, co, n * 2, cudaMemcpyHostToDevice));
+    CU_CHECK_RC(cudaMemcpy(dy + 2 * n, cg, n * 2, cudaMemcpyHostToDevice));
+    ycocg_to_rgb(dy, dy + n, dy + 2 * n, o.as<uint8_t>(), n, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(rgb, o.p, n * 3, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+int alice_codec_wavelet2d_forward(uint8_t wv, int32_t *data, uint32_t w, uint32_t h) {
+    set_error(0, "");
+    return wavelet_nd(wv, false, data, w, h, 1, 2);
+}
+int alice_codec_wavelet2d_inverse(uint8_t wv, int32_t *data, uint32_t w, uint32_t h) {
+    set_error(0, "");
+    return wavelet_nd(wv, true, data, w, h, 1, 2);
+}
+int alice_codec_wavelet3d_forward(uint8_t wv, int32_t *data, uint32_t w, uint32_t h, uint32_t d) {
+    set_error(0, "");
+    return wavelet_nd(wv, false, data, w, h, d, 3);
+}
+int alice_codec_wavelet3d_inverse(uint8_t wv, int32_t *data, uint32_t w, uint32_t h, uint32_t d) {
+    set_error(0, "");
+    return wavelet_nd(wv, true, data, w, h, d, 3);
+}
+
+namespace {
+enum ElemOp { OP_QUANT, OP_FASTQ, OP_DEQUANT };
+int elementwise_i32(ElemOp op, int32_t step, int32_t dz, const int32_t *in, uint64_t n64, int32_t *out,
+                    uint64_t out_len) {
+    set_error(0, "");
+    unsigned long long recip = 0;
+    unsigned shift = 0;
+    if (op == OP_FASTQ) {
+        // FastQuantizer::new (quant.rs:190-217)
+        if (step <= 0) { set_error(kErrQuantStep, "quantization step must be positive"); return kErrQuantStep; }
+        const uint32_t su = (uint32_t)step;
+        const uint32_t extra = 32 - (uint32_t)__builtin_clz(su);
+        shift = 32 + extra;
+        const unsigned __int128 power = (unsigned __int128)1 << shift;
+        recip = (unsigned long long)((power + su - 1) / su);
+    }
+    if (out_len < n64) { set_error(kErrBufferSize, "output smaller than input"); return kErrBufferSize; }
+    const size_t n = (size_t)n64;
+    if (n == 0) return kOk;
+    if (!in || !out) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a, b, flag;
+    if (!a.alloc(n * 4) || !b.alloc(n * 4) || !flag.alloc(4)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, in, n * 4, cudaMemcpyHostToDevice));
+    CU_CHECK_RC(cudaMemset(flag.p, 0, 4));
+    if (op == OP_QUANT) quantize_i32(a.as<int32_t>(), b.as<int32_t>(), n, step, dz, flag.as<int>(), nullptr);
+    else if (op == OP_FASTQ) fast_quantize_i32(a.as<int32_t>(), b.as<int32_t>(), n, dz, recip, shift, nullptr);
+    else dequantize_i32(a.as<int32_t>(), b.as<int32_t>(), n, step, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    int panic = 0;
+    CU_CHECK_RC(cudaMemcpy(&panic, flag.p, 4, cudaMemcpyDeviceToHost));
+    CU_CHECK_RC(cudaMemcpy(out, b.p, n * 4, cudaMemcpyDeviceToHost));
+    if (panic) { set_error(kErrPanic, "division by zero / overflow: the reference panics"); return kErrPanic; }
+    return kOk;
+}
+}  // namespace
+
+int alice_codec_quantize_buffer(int32_t step, int32_t dz, const int32_t *in, uint64_t n, int32_t *out, uint64_t out_len) {
+    return elementwise_i32(OP_QUANT, step, dz, in, n, out, out_len);
+}
+int alice_codec_dequantize_buffer(int32_t step, const int32_t *in, uint64_t n, int32_t *out, uint64_t out_len) {
+    return elementwise_i32(OP_DEQUANT, step, 0, in, n, out, out_len);
+}
+int alice_codec_fast_quantize_buffer(int32_t step, int32_t dz, const int32_t *in, uint64_t n, int32_t *out, uint64_t out_len) {
+    return elementwise_i32(OP_FASTQ, step, dz, in, n, out, out_len);
+}
+
+int alice_codec_to_symbols(const int32_t *coeffs, uint64_t n64, uint8_t *symbols, uint64_t symbols_len) {
+    set_error(0, "");
+    if (symbols_len < n64) { set_error(kErrBufferSize, "symbols smaller than coeffs"); return kErrBufferSize; }
+    const size_t n = (size_t)n64;
+    if (n == 0) return kOk;
+    if (!coeffs || !symbols) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a, b;
+    if (!a.alloc(n * 4) || !b.alloc(n)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, coeffs, n * 4, cudaMemcpyHostToDevice));
+    to_symbols_u8(a.as<int32_t>(), b.as<uint8_t>(), n, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(symbols, b.p, n, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+int alice_codec_from_symbols(const uint8_t *symbols, uint64_t n64, int32_t *coeffs, uint64_t coeffs_len) {
+    set_error(0, "");
+    if (coeffs_len < n64) { set_error(kErrBufferSize, "coeffs smaller than symbols"); return kErrBufferSize; }
+    const size_t n = (size_t)n64;
+    if (n == 0) return kOk;
+    if (!coeffs || !symbols) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a, b;
+    if (!a.alloc(n) || !b.alloc(n * 4)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, symbols, n, cudaMemcpyHostToDevice));
+    from_symbols_i32(a.as<uint8_t>(), b.as<int32_t>(), n, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(coeffs, b.p, n * 4, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+int alice_codec_build_histogram(const uint8_t *symbols, uint64_t n64, uint32_t *hist256) {
+    set_error(0, "");
+    if (!hist256) { set_error(kErrNull, "null argument"); return kErrNull; }
+    const size_t n = (size_t)n64;
+    if (n == 0) { memset(hist256, 0, 1024); return kOk; }
+    if (!symbols) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a, h;
+    if (!a.alloc(n) || !h.alloc(1024)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, symbols, n, cudaMemcpyHostToDevice));
+    CU_CHECK_RC(cudaMemset(h.p, 0, 1024));
+    histogram_u8(a.as<uint8_t>(), n, h.as<unsigned>(), nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(hist256, h.p, 1024, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+double alice_codec_rdo_bpp_from_quality(uint8_t quality) {
+    // quant.rs:398-412 — scalar host arithmetic on the configuration byte
+    const double RCP_100 = 1.0 / 100.0;
+    if (quality > 100) quality = 100;
+    double q = (double)quality * RCP_100;
+    return fma(q * q, 23.9, 0.1);
+}
+int alice_codec_rdo_compute_quantizer(double target_bpp, const int32_t *coeffs, uint64_t n64, uint8_t subband,
+                                      int32_t *step, int32_t *dead_zone) {
+    set_error(0, "");
+    if (subband > 7 || !step || !dead_zone) { set_error(kErrNull, "bad subband or null output"); return kErrNull; }
+    const size_t n = (size_t)n64;
+    double variance = 1.0;  // quant.rs:416-418
+    if (n > 0) {
+        if (!coeffs) { set_error(kErrNull, "null argument"); return kErrNull; }
+        if (!cuda_ready()) return kErrCuda;
+        DevBuf a, s, v;
+        if (!a.alloc(n * 4) || !s.alloc(8) || !v.alloc(8)) return kErrCuda;
+        CU_CHECK_RC(cudaMemcpy(a.p, coeffs, n * 4, cudaMemcpyHostToDevice));
+        CU_CHECK_RC(cudaMemset(s.p, 0, 8));
+        sum_i64(a.as<int32_t>(), n, s.as<long long>(), nullptr);
+        long long sum = 0;
+        CU_CHECK_RC(cudaMemcpy(&sum, s.p, 8, cudaMemcpyDeviceToHost));
+        const double inv_n = 1.0 / (double)n;
+        const double mean = (double)sum * inv_n;
+        variance_seq_f64(a.as<int32_t>(), n, mean, v.as<double>(), nullptr);
+        CU_CHECK_RC(cudaGetLastError());
+        double acc = 0;
+        CU_CHECK_RC(cudaMemcpy(&acc, v.p, 8, cudaMemcpyDeviceToHost));
+        variance = acc * inv_n;
+        if (!(variance > 1.0)) variance = 1.0;  // f64::max(1.0)
+    }
+    // quant.rs:440-468 — closed form on two scalars
+    const double ln2 = 0.693147180559945309417232121458176568;
+    const double lambda = (6.0 * ln2 * variance) / target_bpp;
+    const double r = round(sqrt(12.0 * lambda));
+    int32_t base;
+    if (r != r) base = 0;
+    else if (r >= 2147483647.0) base = INT32_MAX;
+    else if (r <= -2147483648.0) base = INT32_MIN;
+    else base = (int32_t)r;
+    if (base < 1) base = 1;
+    static const int strength[8] = {1, 2, 2, 4, 2, 4, 4, 8};  // lib.rs:152-159
+    int32_t st = (int32_t)((uint32_t)base * (uint32_t)strength[subband]);
+    if (st < 1) st = 1;
+    *step = st;
+    *dead_zone = (int32_t)((uint32_t)st + (uint32_t)(st / 2));
+    return kOk;
+}
+
+int alice_codec_freq_table_from_histogram(const uint32_t *hist, uint32_t n_symbols, uint16_t *cum256,
+                                          uint16_t *freq256, uint8_t *lut4096) {
+    set_error(0, "");
+    if (!hist) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (n_symbols == 0) { set_error(kErrPanic, "empty histogram: the reference divides by zero"); return kErrPanic; }
+    if (n_symbols > 256) { set_error(kErrDimensions, "n_symbols > 256"); return kErrDimensions; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf h, enc, dec, aux, fr, cu, l8;
+    if (!h.alloc(1024) || !enc.alloc(kEncTableBytes) || !dec.alloc(kDecLutEntries * 4) || !aux.alloc(sizeof(DecAux)) ||
+        !fr.alloc(512) || !cu.alloc(512) || !l8.alloc(4096))
+        return kErrCuda;
+    CU_CHECK_RC(cudaMemset(h.p, 0, 1024));
+    CU_CHECK_RC(cudaMemcpy(h.p, hist, n_symbols * 4, cudaMemcpyHostToDevice));
+    build_tables(h.as<unsigned>(), 1, (int)n_symbols, enc.as<EncSym>(), dec.as<uint32_t>(), aux.as<DecAux>(),
+                 fr.as<uint16_t>(), cu.as<uint16_t>(), l8.as<uint8_t>(), nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    if (freq256) CU_CHECK_RC(cudaMemcpy(freq256, fr.p, 512, cudaMemcpyDeviceToHost));
+    if (cum256) CU_CHECK_RC(cudaMemcpy(cum256, cu.p, 512, cudaMemcpyDeviceToHost));
+    if (lut4096) CU_CHECK_RC(cudaMemcpy(lut4096, l8.p, 4096, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+int alice_codec_rans_encode(const uint8_t *symbols, uint64_t n64, const uint32_t *hist, uint32_t n_symbols,
+                            uint8_t **out, uint64_t *out_len) {
+    set_error(0, "");
+    if (!hist || !out || !out_len || (n64 && !symbols)) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (n_symbols == 0) { set_error(kErrPanic, "empty histogram"); return kErrPanic; }
+    if (n_symbols > 256) { set_error(kErrDimensions, "n_symbols > 256"); return kErrDimensions; }
+    const size_t n = (size_t)n64;
+    for (size_t i = 0; i < n; i++)
+        if (symbols[i] >= n_symbols) {  // table.get_symbol would index out of bounds (rans.rs:195)
+            set_error(kErrPanic, "symbol outside the table");
+            return kErrPanic;
+        }
+    if (!cuda_ready()) return kErrCuda;
+    const size_t cap = (2 * n + 4 + 15) / 16 * 16;
+    DevBuf h, enc, dec, aux, sy, pay, job, res;
+    if (!h.alloc(1024) || !enc.alloc(kEncTableBytes) || !dec.alloc(kDecLutEntries * 4) || !aux.alloc(sizeof(DecAux)) ||
+        !sy.alloc(n) || !pay.alloc(cap) || !job.alloc(sizeof(RansEncJob)) || !res.alloc(16))
+        return kErrCuda;
+    CU_CHECK_RC(cudaMemset(h.p, 0, 1024));
+    CU_CHECK_RC(cudaMemcpy(h.p, hist, n_symbols * 4, cudaMemcpyHostToDevice));
+    if (n) CU_CHECK_RC(cudaMemcpy(sy.p, symbols, n, cudaMemcpyHostToDevice));
+    build_tables(h.as<unsigned>(), 1, (int)n_symbols, enc.as<EncSym>(), dec.as<uint32_t>(), aux.as<DecAux>(), nullptr,
+                 nullptr, nullptr, nullptr);
+    RansEncJob j;
+    j.symbols = sy.as<uint8_t>(); j.n = n; j.out = pay.as<uint8_t>(); j.cap = cap;
+    CU_CHECK_RC(cudaMemcpy(job.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    rans_encode(job.as<RansEncJob>(), enc.as<EncSym>(), nullptr, res.as<unsigned long long>(), 1, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    unsigned long long r[2] = {0, 0};
+    CU_CHECK_RC(cudaMemcpy(r, res.p, 16, cudaMemcpyDeviceToHost));
+    if (r[1] & 2) { set_error(kErrPanic, "symbol with zero frequency in use: the reference aborts"); return kErrPanic; }
+    if (r[1]) { set_error(kErrCuda, "rANS output overflow"); return kErrCuda; }
+    uint8_t *p = (uint8_t *)malloc((size_t)r[0] ? (size_t)r[0] : 1);
+    if (!p) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
+    CU_CHECK_RC(cudaMemcpy(p, pay.as<uint8_t>() + cap - r[0], (size_t)r[0], cudaMemcpyDeviceToHost));
+    *out = p;
+    *out_len = r[0];
+    return kOk;
+}
+
+int alice_codec_rans_decode(const uint8_t *stream, uint64_t len64, const uint32_t *hist, uint32_t n_symbols,
+                            uint8_t *symbols_out, uint64_t n64) {
+    set_error(0, "");
+    if (!hist || (n64 && !symbols_out) || (len64 && !stream)) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (n_symbols == 0) { set_error(kErrPanic, "empty histogram"); return kErrPanic; }
+    if (n_symbols > 256) { set_error(kErrDimensions, "n_symbols > 256"); return kErrDimensions; }
+    const size_t n = (size_t)n64, len = (size_t)len64;
+    if (n == 0) return kOk;
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf h, enc, dec, aux, sy, in, job;
+    if (!h.alloc(1024) || !enc.alloc(kEncTableBytes) || !dec.alloc(kDecLutEntries * 4) || !aux.alloc(sizeof(DecAux)) ||
+        !sy.alloc(n) || !in.alloc(len) || !job.alloc(sizeof(RansDecJob)))
+        return kErrCuda;
+    CU_CHECK_RC(cudaMemset(h.p, 0, 1024));
+    CU_CHECK_RC(cudaMemcpy(h.p, hist, n_symbols * 4, cudaMemcpyHostToDevice));
+    if (len) CU_CHECK_RC(cudaMemcpy(in.p, stream, len, cudaMemcpyHostToDevice));
+    build_tables(h.as<unsigned>(), 1, (int)n_symbols, enc.as<EncSym>(), dec.as<uint32_t>(), aux.as<DecAux>(), nullptr,
+                 nullptr, nullptr, nullptr);
+    RansDecJob j;
+    j.in = in.as<uint8_t>(); j.len = len; j.symbols = sy.as<uint8_t>(); j.n = n;
+    CU_CHECK_RC(cudaMemcpy(job.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    rans_decode(job.as<RansDecJob>(), dec.as<uint32_t>(), aux.as<DecAux>(), 1, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(symbols_out, sy.p, n, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
+EncodedChunk *alice_codec_encode_stages(const FrameEncoder *enc, const uint8_t *rgb, uint64_t rgb_len, uint32_t w,
+                                        uint32_t h, uint32_t f, int32_t *coeffs_out, uint8_t *symbols_out) {
+    return encode_impl(enc, rgb, rgb_len, w, h, f, coeffs_out, symbols_out);
+}
+uint8_t *alice_codec_decode_stages(const EncodedChunk *chunk, uint64_t *out_len, uint8_t *symbols_out) {
+    return decode_impl(chunk, out_len, symbols_out);
+}
+
+// ------------------------------------------------------------------------------ batch API
+AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t w, uint32_t h, uint32_t f,
+                                     uint32_t n_chunks, void *cuda_stream) {
+    set_error(0, "");
+    if (wavelet > 2 || n_chunks == 0) { set_error(kErrDimensions, "bad wavelet byte or n_chunks == 0"); return nullptr; }
+    Dims d;
+    if (make_dims(w, h, f, d)) return nullptr;
+    if (d.n_pixels == 0 || d.padded > 0xffffffffull) { set_error(kErrDimensions, "empty or oversized shape"); return nullptr; }
+    if (!cuda_ready()) return nullptr;
+    AliceBatch *b = new (std::nothrow) AliceBatch();
+    if (!b) return nullptr;
+    // single chunks keep the worst-case payload capacity; batches budget N/2 + 64 KiB per stream and fall
+    // back to a worst-case buffer for any stream that overflows (Engine::run_rans_encode)
+    const uint64_t cap = n_chunks == 1 ? 0 : d.padded / 2 + 65536;
+    b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false);
+    if (!b->eng || !b->eng->ok()) { delete b->eng; delete b; return nullptr; }
+    b->quality = quality;
+    b->wavelet = wavelet;
+    return b;
+}
+void alice_codec_batch_destroy(AliceBatch *b) {
+    if (!b) return;
+    delete b->eng;
+    delete b;
+}
+int alice_codec_batch_encode_device(AliceBatch *b, const uint8_t *const *d_rgb, uint32_t n) {
+    set_error(0, "");
+    if (!b || !d_rgb) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->encode_device(b->quality, b->wavelet, d_rgb, n, nullptr);
+}
+int alice_codec_batch_decode_device(AliceBatch *b, uint8_t *const *d_rgb_out, uint32_t n) {
+    set_error(0, "");
+    if (!b || !d_rgb_out) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->decode_device_resident(d_rgb_out, n);
+}
+EncodedChunk *alice_codec_batch_get_chunk(AliceBatch *b, uint32_t i) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return nullptr; }
+    EncodedChunk *c = new (std::nothrow) EncodedChunk();
+    if (!c) return nullptr;
+    if (b->eng->fetch_chunk(i, c->c)) { delete c; return nullptr; }
+    return c;
+}
+int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, uint32_t n, EncodedChunk **out_chunks) {
+    set_error(0, "");
+    if (!b || !h_rgb || !out_chunks) { set_error(kErrNull, "null argument"); return kErrNull; }
+    Engine *e = b->eng;
+    if (n > e->cap_chunks()) { set_error(kErrBufferSize, "batch larger than capacity"); return kErrBufferSize; }
+    const size_t bytes = (size_t)e->dims().n_pixels * 3;
+    b->stage_ptrs.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t *s = e->rgb_stage(i);
+        if (!s) return kErrCuda;
+        b->stage_ptrs[i] = s;
+        CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
+    }
+    int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++) {
+        out_chunks[i] = alice_codec_batch_get_chunk(b, i);
+        if (!out_chunks[i]) {
+            for (uint32_t k = 0; k < i; k++) { delete out_chunks[k]; out_chunks[k] = nullptr; }
+            return last_error_code() ? last_error_code() : kErrCuda;
+        }
+    }
+    return kOk;
+}
+int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chunks, uint32_t n,
+                                  uint8_t *const *h_rgb_out) {
+    set_error(0, "");
+    if (!b || !chunks || !h_rgb_out) { set_error(kErrNull, "null argument"); return kErrNull; }
+    Engine *e = b->eng;
+    if (n > e->cap_chunks()) { set_error(kErrBufferSize, "batch larger than capacity"); return kErrBufferSize; }
+    const size_t bytes = (size_t)e->dims().n_pixels * 3;
+    std::vector<const Chunk *> cks(n);
+    b->stage_ptrs.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!chunks[i]) { set_error(kErrNull, "null chunk"); return kErrNull; }
+        cks[i] = &chunks[i]->c;
+        uint8_t *s = e->rgb_stage(i);
+        if (!s) return kErrCuda;
+        b->stage_ptrs[i] = s;
+    }
+    int rc = e->decode_chunks(cks.data(), n, b->stage_ptrs.data());
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++)
+        CU_CHECK_RC(cudaMemcpyAsync(h_rgb_out[i], b->stage_ptrs[i], bytes, cudaMemcpyDeviceToHost, e->stream()));
+    CU_CHECK_RC(cudaStreamSynchronize(e->stream()));
+    return kOk;
+}
+int alice_codec_batch_timings(AliceBatch *b, float *ms8) {
+    if (!b || !ms8) return kErrNull;
+    memcpy(ms8, b->eng->timings.ms, sizeof(float) * 8);
+    return kOk;
+}
+uint64_t alice_codec_batch_device_bytes(const AliceBatch *b) { return b ? b->eng->device_bytes() : 0; }
+
+int alice_codec_synth_rgb_device(int kind, uint32_t seed, uint32_t w, uint32_t h, uint32_t f, uint8_t *d_rgb,
+                                 void *cuda_stream) {
+    set_error(0, "");
+    if (!d_rgb) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    synth_rgb(kind, seed, (int)w, (int)h, (int)f, d_rgb, (cudaStream_t)cuda_stream);
+    CU_CHECK_RC(cudaGetLastError());
+    return kOk;
+}
+void *alice_codec_pinned_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); set_error(kErrCuda, "pinned allocation failed"); return nullptr; }
+    return p;
+}
+void alice_codec_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+int alice_codec_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int alice_codec_set_device(int device) {
+    CU_CHECK_RC(cudaSetDevice(device));
+    return kOk;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

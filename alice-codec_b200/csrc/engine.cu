@@ -1,0 +1,443 @@
+// engine.cu — host orchestration of the encode / decode pipeline on one CUDA device.
+// See engine.h for the mapping to src/pipeline.rs.
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+namespace alice {
+
+// ------------------------------------------------------------------------------- errors
+static thread_local int t_err_code = 0;
+static thread_local std::string t_err_msg;
+void set_error(int code, const std::string &msg) { t_err_code = code; t_err_msg = msg; }
+int last_error_code() { return t_err_code; }
+const char *last_error_msg() { return t_err_msg.c_str(); }
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            set_error(kErrCuda, std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+            return kErrCuda;                                                                          \
+        }                                                                                             \
+    } while (0)
+
+bool cuda_ready() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error(kErrCuda, std::string("no usable CUDA device: ") +
+                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                " (libalice_codec has no CPU fallback)");
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------- .alc container
+static void put_u32(std::vector<uint8_t> &b, uint32_t v) {
+    b.push_back((uint8_t)v); b.push_back((uint8_t)(v >> 8)); b.push_back((uint8_t)(v >> 16)); b.push_back((uint8_t)(v >> 24));
+}
+static uint32_t get_u32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+std::vector<uint8_t> Chunk::to_bytes() const {
+    std::vector<uint8_t> buf;
+    buf.reserve(kFixedHeaderBytes + 3 * kChannelHeaderBytes + data.size());
+    buf.push_back('A'); buf.push_back('L'); buf.push_back('C'); buf.push_back('C');
+    buf.push_back(1);  // FORMAT_VERSION, pipeline.rs:145
+    buf.push_back(wavelet);
+    put_u32(buf, width);
+    put_u32(buf, height);
+    put_u32(buf, frames);
+    for (const ChannelHeader &c : ch) {
+        put_u32(buf, c.compressed_len);
+        put_u32(buf, (uint32_t)c.quant_step);
+        put_u32(buf, (uint32_t)c.quant_dead_zone);
+        put_u32(buf, c.num_symbols);
+        for (uint32_t v : c.histogram) put_u32(buf, v);
+    }
+    buf.insert(buf.end(), data.begin(), data.end());
+    return buf;
+}
+
+int Chunk::from_bytes(const uint8_t *p, size_t len, Chunk &out) {
+    const size_t min_len = kFixedHeaderBytes + 3 * kChannelHeaderBytes;
+    if (len < min_len) { set_error(kErrBitstream, "data too short"); return kErrBitstream; }
+    if (memcmp(p, "ALCC", 4) != 0) { set_error(kErrBitstream, "bad magic (expected ALCC)"); return kErrBitstream; }
+    if (p[4] != 1) { set_error(kErrBitstream, "unsupported version"); return kErrBitstream; }
+    if (p[5] > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return kErrBitstream; }
+    out.wavelet = p[5];
+    out.width = get_u32(p + 6);
+    out.height = get_u32(p + 10);
+    out.frames = get_u32(p + 14);
+    size_t off = kFixedHeaderBytes;
+    size_t total = 0;
+    for (ChannelHeader &c : out.ch) {
+        c.compressed_len = get_u32(p + off); off += 4;
+        c.quant_step = (int32_t)get_u32(p + off); off += 4;
+        c.quant_dead_zone = (int32_t)get_u32(p + off); off += 4;
+        c.num_symbols = get_u32(p + off); off += 4;
+        for (uint32_t &v : c.histogram) { v = get_u32(p + off); off += 4; }
+        total += c.compressed_len;
+    }
+    if (len < off + total) { set_error(kErrBitstream, "truncated payload"); return kErrBitstream; }
+    out.data.assign(p + off, p + off + total);  // trailing bytes are ignored, pipeline.rs:303
+    return kOk;
+}
+
+int make_dims(uint32_t w, uint32_t h, uint32_t f, Dims &d) {
+    unsigned __int128 p = (unsigned __int128)w * h;
+    p *= f;
+    if (p > (unsigned __int128)UINT64_MAX) { set_error(kErrOverflow, "dimensions overflow usize"); return kErrOverflow; }
+    d.w = w; d.h = h; d.f = f;
+    d.n_pixels = (uint64_t)p;
+    d.pw = w + (w & 1);
+    d.ph = h + (h & 1);
+    d.pf = (f == 1) ? 2 : f + (f & 1);
+    unsigned __int128 pp = (unsigned __int128)d.pw * d.ph * d.pf;
+    d.padded = pp > (unsigned __int128)UINT64_MAX ? UINT64_MAX : (uint64_t)pp;
+    return kOk;
+}
+
+int quality_to_step(uint8_t quality) {
+    int q = quality > 100 ? 100 : quality;
+    int s = 64 - (q * 63) / 100;
+    return s < 1 ? 1 : s;
+}
+
+// -------------------------------------------------------------------------------- Engine
+template <class T> static bool dev_alloc(T *&p, size_t bytes, uint64_t &acc) {
+    void *q = nullptr;
+    if (cudaMalloc(&q, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+    p = reinterpret_cast<T *>(q);
+    acc += bytes;
+    return true;
+}
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStream_t user_stream, bool own_stream)
+    : d_(d), cap_(cap_chunks), own_stream_(own_stream) {
+    const size_t N = (size_t)d_.padded;
+    const size_t vol = (size_t)d_.f * d_.ph * d_.pw;
+    pay_cap_ = round_up(payload_cap ? (size_t)payload_cap : 2 * N + 4, 16);
+    const size_t S = (size_t)cap_ * 3;
+    if (own_stream_) {
+        if (cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
+    } else st_ = user_stream;
+    bool a = true;
+    a = a && dev_alloc(d_scratch_, vol * 3 * 4, dev_bytes_);
+    a = a && dev_alloc(d_symbols_, S * N, dev_bytes_);
+    a = a && dev_alloc(d_hist_, S * 256 * sizeof(unsigned), dev_bytes_);
+    a = a && dev_alloc(d_enc_, S * 256 * sizeof(EncSym), dev_bytes_);
+    a = a && dev_alloc(d_dec_lut_, S * kDecLutEntries * sizeof(uint32_t), dev_bytes_);
+    a = a && dev_alloc(d_aux_, S * sizeof(DecAux), dev_bytes_);
+    a = a && dev_alloc(d_payload_, S * pay_cap_, dev_bytes_);
+    a = a && dev_alloc(d_enc_jobs_, S * sizeof(RansEncJob), dev_bytes_);
+    a = a && dev_alloc(d_dec_jobs_, S * sizeof(RansDecJob), dev_bytes_);
+    a = a && dev_alloc(d_results_, S * 2 * sizeof(unsigned long long), dev_bytes_);
+    a = a && cudaMallocHost((void **)&h_results_, S * 2 * sizeof(unsigned long long)) == cudaSuccess;
+    a = a && cudaMallocHost((void **)&h_hist_, S * 256 * sizeof(unsigned)) == cudaSuccess;
+    a = a && cudaMallocHost((void **)&h_enc_jobs_, S * sizeof(RansEncJob)) == cudaSuccess;
+    a = a && cudaMallocHost((void **)&h_dec_jobs_, S * sizeof(RansDecJob)) == cudaSuccess;
+    for (auto &e : ev_) a = a && cudaEventCreate(&e) == cudaSuccess;
+    if (!a) { cudaGetLastError(); set_error(kErrCuda, "device or pinned memory allocation failed"); return; }
+    overflow_bufs_.assign(S, nullptr);
+    stream_off_.assign(S, 0);
+    stream_len_.assign(S, 0);
+    stream_base_.assign(S, nullptr);
+    ok_ = true;
+}
+
+Engine::~Engine() {
+    if (st_ && own_stream_) cudaStreamSynchronize(st_);
+    cudaFree(d_scratch_); cudaFree(d_symbols_); cudaFree(d_hist_); cudaFree(d_enc_); cudaFree(d_dec_lut_);
+    cudaFree(d_aux_); cudaFree(d_payload_); cudaFree(d_enc_jobs_); cudaFree(d_dec_jobs_); cudaFree(d_results_);
+    for (uint8_t *p : rgb_stage_) cudaFree(p);
+    for (uint8_t *p : overflow_bufs_) if (p) cudaFree(p);
+    if (h_results_) cudaFreeHost(h_results_);
+    if (h_hist_) cudaFreeHost(h_hist_);
+    if (h_enc_jobs_) cudaFreeHost(h_enc_jobs_);
+    if (h_dec_jobs_) cudaFreeHost(h_dec_jobs_);
+    for (auto &e : ev_) if (e) cudaEventDestroy(e);
+    if (st_ && own_stream_) cudaStreamDestroy(st_);
+    cudaGetLastError();
+}
+
+uint8_t *Engine::rgb_stage(uint32_t slot) {
+    while (rgb_stage_.size() <= slot) {
+        uint8_t *p = nullptr;
+        if (!dev_alloc(p, (size_t)d_.n_pixels * 3, dev_bytes_)) {
+            set_error(kErrCuda, "device memory allocation failed (rgb staging)");
+            return nullptr;
+        }
+        rgb_stage_.push_back(p);
+    }
+    return rgb_stage_[slot];
+}
+
+int Engine::run_rans_encode(uint32_t n) {
+    const size_t N = (size_t)d_.padded;
+    const uint32_t S = n * 3;
+    for (uint32_t s = 0; s < S; s++) {
+        h_enc_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+        h_enc_jobs_[s].n = N;
+        h_enc_jobs_[s].out = d_payload_ + (size_t)s * pay_cap_;
+        h_enc_jobs_[s].cap = pay_cap_;
+        stream_base_[s] = h_enc_jobs_[s].out;
+    }
+    CU_TRY(cudaMemcpyAsync(d_enc_jobs_, h_enc_jobs_, S * sizeof(RansEncJob), cudaMemcpyHostToDevice, st_));
+    rans_encode(d_enc_jobs_, d_enc_, d_hist_, d_results_, (int)S, st_);
+    CU_TRY(cudaEventRecord(ev_[3], st_));
+    CU_TRY(cudaMemcpyAsync(h_results_, d_results_, S * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
+    CU_TRY(cudaMemcpyAsync(h_hist_, d_hist_, (size_t)S * 256 * sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+    CU_TRY(cudaStreamSynchronize(st_));
+    CU_TRY(cudaGetLastError());
+    for (uint32_t s = 0; s < S; s++) {
+        unsigned long long status = h_results_[2 * s + 1];
+        if (status & 2) {
+            set_error(kErrPanic, "symbol with zero frequency in use: the reference aborts on this input");
+            return kErrPanic;
+        }
+        if (status & 1) {
+            // payload did not fit the per-stream capacity: redo this stream into a worst-case buffer
+            const size_t full = round_up(2 * N + 4, 16);
+            if (!overflow_bufs_[s]) {
+                if (!dev_alloc(overflow_bufs_[s], full, dev_bytes_)) {
+                    set_error(kErrCuda, "device memory allocation failed (rANS overflow buffer)");
+                    return kErrCuda;
+                }
+            }
+            h_enc_jobs_[s].out = overflow_bufs_[s];
+            h_enc_jobs_[s].cap = full;
+            stream_base_[s] = overflow_bufs_[s];
+            CU_TRY(cudaMemcpyAsync(d_enc_jobs_ + s, h_enc_jobs_ + s, sizeof(RansEncJob), cudaMemcpyHostToDevice, st_));
+            rans_encode(d_enc_jobs_ + s, d_enc_ + (size_t)s * 256, d_hist_, d_results_ + 2 * s, 1, st_);
+            CU_TRY(cudaMemcpyAsync(h_results_ + 2 * s, d_results_ + 2 * s, 2 * sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, st_));
+            CU_TRY(cudaStreamSynchronize(st_));
+            if (h_results_[2 * s + 1] != 0) { set_error(kErrCuda, "rANS retry failed"); return kErrCuda; }
+        }
+        stream_len_[s] = h_results_[2 * s];
+        stream_off_[s] = h_enc_jobs_[s].cap - stream_len_[s];
+    }
+    return kOk;
+}
+
+int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const *d_rgb, uint32_t n,
+                          int32_t *d_coef_dump) {
+    if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    const size_t N = (size_t)d_.padded;
+    const int step = quality_to_step(quality);
+    last_wavelet = wavelet;
+    last_step = step;
+    last_n = n;
+    CU_TRY(cudaMemsetAsync(d_hist_, 0, (size_t)n * 3 * 256 * sizeof(unsigned), st_));
+    CU_TRY(cudaEventRecord(ev_[0], st_));
+    for (uint32_t c = 0; c < n; c++)
+        forward_frontend(wavelet, d_rgb[c], reinterpret_cast<int16_t *>(d_scratch_), d_symbols_ + (size_t)c * 3 * N,
+                         d_hist_ + (size_t)c * 3 * 256, (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph,
+                         (int)d_.pf, step, c == 0 ? d_coef_dump : nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[1], st_));
+    build_tables(d_hist_, (int)n * 3, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[2], st_));
+    int rc = run_rans_encode(n);
+    if (rc) return rc;
+    cudaEventElapsedTime(&timings.ms[0], ev_[0], ev_[1]);
+    cudaEventElapsedTime(&timings.ms[1], ev_[1], ev_[2]);
+    cudaEventElapsedTime(&timings.ms[2], ev_[2], ev_[3]);
+    return kOk;
+}
+
+int Engine::fetch_chunk(uint32_t i, Chunk &out) {
+    if (i >= last_n) { set_error(kErrBufferSize, "chunk index out of range"); return kErrBufferSize; }
+    out.width = d_.w; out.height = d_.h; out.frames = d_.f;
+    out.wavelet = last_wavelet;
+    size_t total = 0;
+    for (int c = 0; c < 3; c++) {
+        const uint32_t s = i * 3 + c;
+        ChannelHeader &h = out.ch[c];
+        h.compressed_len = (uint32_t)stream_len_[s];
+        h.quant_step = last_step;
+        h.quant_dead_zone = last_step;          // Quantizer::new: dead_zone = step (quant.rs:70-75)
+        h.num_symbols = (uint32_t)d_.padded;    // `as u32`, pipeline.rs:492
+        memcpy(h.histogram, h_hist_ + (size_t)s * 256, 256 * sizeof(uint32_t));
+        total += stream_len_[s];
+    }
+    out.data.resize(total);
+    size_t off = 0;
+    for (int c = 0; c < 3; c++) {
+        const uint32_t s = i * 3 + c;
+        if (stream_len_[s])
+            CU_TRY(cudaMemcpyAsync(out.data.data() + off, stream_base_[s] + stream_off_[s], stream_len_[s],
+                                   cudaMemcpyDeviceToHost, st_));
+        off += stream_len_[s];
+    }
+    CU_TRY(cudaStreamSynchronize(st_));
+    return kOk;
+}
+
+int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
+    if (n > last_n) { set_error(kErrBufferSize, "decode_device: more chunks than the last encode"); return kErrBufferSize; }
+    const size_t N = (size_t)d_.padded;
+    const uint32_t S = n * 3;
+    CU_TRY(cudaEventRecord(ev_[4], st_));
+    build_tables(d_hist_, (int)S, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[5], st_));
+    for (uint32_t s = 0; s < S; s++) {
+        h_dec_jobs_[s].in = stream_base_[s] + stream_off_[s];
+        h_dec_jobs_[s].len = stream_len_[s];
+        h_dec_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+        h_dec_jobs_[s].n = N;
+    }
+    CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
+    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
+    CU_TRY(cudaEventRecord(ev_[6], st_));
+    const int steps[3] = {last_step, last_step, last_step};
+    for (uint32_t c = 0; c < n; c++)
+        inverse_backend(last_wavelet, d_symbols_ + (size_t)c * 3 * N, reinterpret_cast<int32_t *>(d_scratch_),
+                        d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
+    CU_TRY(cudaEventRecord(ev_[7], st_));
+    CU_TRY(cudaStreamSynchronize(st_));
+    CU_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&timings.ms[3], ev_[4], ev_[5]);
+    cudaEventElapsedTime(&timings.ms[4], ev_[5], ev_[6]);
+    cudaEventElapsedTime(&timings.ms[5], ev_[6], ev_[7]);
+    return kOk;
+}
+
+int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out) {
+    if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    const size_t N = (size_t)d_.padded;
+    const uint32_t S = n * 3;
+    // validation, in the reference's order (pipeline.rs:562-579)
+    for (uint32_t i = 0; i < n; i++) {
+        const Chunk &ck = *chunks[i];
+        if (ck.width != d_.w || ck.height != d_.h || ck.frames != d_.f) {
+            set_error(kErrDimensions, "chunk shape differs from the engine's");
+            return kErrDimensions;
+        }
+        size_t off = 0;
+        for (int c = 0; c < 3; c++) {
+            if ((uint64_t)ck.ch[c].num_symbols != d_.padded) {
+                set_error(kErrBitstream, "num_symbols != padded_pixels");
+                return kErrBitstream;
+            }
+            if (off + ck.ch[c].compressed_len > ck.data.size()) {
+                set_error(kErrBitstream, "compressed data overrun");
+                return kErrBitstream;
+            }
+            off += ck.ch[c].compressed_len;
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        const Chunk &ck = *chunks[i];
+        size_t off = 0;
+        for (int c = 0; c < 3; c++) {
+            const uint32_t s = i * 3 + c;
+            memcpy(h_hist_ + (size_t)s * 256, ck.ch[c].histogram, 256 * sizeof(uint32_t));
+            const size_t len = ck.ch[c].compressed_len;
+            uint8_t *dst = d_payload_ + (size_t)s * pay_cap_;
+            if (len > pay_cap_) {
+                const size_t full = round_up(std::max(len, 2 * N + 4), 16);
+                if (overflow_bufs_[s]) { cudaFree(overflow_bufs_[s]); overflow_bufs_[s] = nullptr; }
+                if (!dev_alloc(overflow_bufs_[s], full, dev_bytes_)) {
+                    set_error(kErrCuda, "device memory allocation failed (payload)");
+                    return kErrCuda;
+                }
+                dst = overflow_bufs_[s];
+            }
+            if (len) CU_TRY(cudaMemcpyAsync(dst, ck.data.data() + off, len, cudaMemcpyHostToDevice, st_));
+            off += len;
+            h_dec_jobs_[s].in = dst;
+            h_dec_jobs_[s].len = len;
+            h_dec_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+            h_dec_jobs_[s].n = N;
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(d_hist_, h_hist_, (size_t)S * 256 * sizeof(unsigned), cudaMemcpyHostToDevice, st_));
+    CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
+    CU_TRY(cudaEventRecord(ev_[4], st_));
+    build_tables(d_hist_, (int)S, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[5], st_));
+    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
+    CU_TRY(cudaEventRecord(ev_[6], st_));
+    for (uint32_t i = 0; i < n; i++) {
+        const Chunk &ck = *chunks[i];
+        const int steps[3] = {ck.ch[0].quant_step, ck.ch[1].quant_step, ck.ch[2].quant_step};
+        inverse_backend(ck.wavelet, d_symbols_ + (size_t)i * 3 * N, reinterpret_cast<int32_t *>(d_scratch_),
+                        d_rgb_out[i], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
+    }
+    CU_TRY(cudaEventRecord(ev_[7], st_));
+    CU_TRY(cudaStreamSynchronize(st_));
+    CU_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&timings.ms[3], ev_[4], ev_[5]);
+    cudaEventElapsedTime(&timings.ms[4], ev_[5], ev_[6]);
+    cudaEventElapsedTime(&timings.ms[5], ev_[6], ev_[7]);
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------ the pool
+namespace {
+struct PoolEntry {
+    std::unique_ptr<Engine> eng;
+    int device = 0;
+    bool busy = false;
+    uint64_t stamp = 0;
+};
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+uint64_t g_stamp = 0;
+constexpr size_t kMaxIdleEngines = 2;
+}  // namespace
+
+Engine *acquire_engine(const Dims &d) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (PoolEntry &p : g_pool)
+        if (!p.busy && p.device == dev && p.eng->dims().w == d.w && p.eng->dims().h == d.h && p.eng->dims().f == d.f) {
+            p.busy = true;
+            p.stamp = ++g_stamp;
+            return p.eng.get();
+        }
+    // drop idle engines of other shapes beyond the cap (oldest first) before allocating a new one
+    for (;;) {
+        size_t idle = 0, oldest = g_pool.size();
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (!g_pool[i].busy) {
+                idle++;
+                if (oldest == g_pool.size() || g_pool[i].stamp < g_pool[oldest].stamp) oldest = i;
+            }
+        if (idle < kMaxIdleEngines || oldest == g_pool.size()) break;
+        g_pool.erase(g_pool.begin() + (long)oldest);
+    }
+    std::unique_ptr<Engine> e(new Engine(d, 1, 0, nullptr, true));
+    if (!e->ok()) {
+        // out of memory: release every idle engine and retry once
+        for (size_t i = g_pool.size(); i-- > 0;)
+            if (!g_pool[i].busy) g_pool.erase(g_pool.begin() + (long)i);
+        e.reset(new Engine(d, 1, 0, nullptr, true));
+        if (!e->ok()) return nullptr;
+    }
+    PoolEntry p;
+    p.eng = std::move(e);
+    p.device = dev;
+    p.busy = true;
+    p.stamp = ++g_stamp;
+    g_pool.push_back(std::move(p));
+    return g_pool.back().eng.get();
+}
+
+void release_engine(Engine *e) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (PoolEntry &p : g_pool)
+        if (p.eng.get() == e) p.busy = false;
+}
+
+}  // namespace alice

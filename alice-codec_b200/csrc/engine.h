@@ -1,0 +1,124 @@
+// engine.h — host-side pipeline objects of libalice_codec.
+//
+//   Chunk         = EncodedChunk (src/pipeline.rs:172-185) with its three ChannelHeaders
+//                   (:123-134) and the .alc (de)serialisation (:200-226, :235-313).
+//   Engine        = device buffers + CUDA stream for up to `cap_chunks` chunks of one shape
+//                   in flight; runs FrameEncoder::encode (:377-507) and FrameDecoder::decode
+//                   (:537-624) on the device for each of them.
+// Errors are CodecError variants (src/error.rs:12-23) carried as ALICE_ERR_* codes.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace alice {
+
+constexpr int kOk = 0, kErrBufferSize = 1, kErrDimensions = 2, kErrOverflow = 3, kErrBitstream = 4,
+              kErrQuantStep = 5, kErrPanic = 6, kErrNull = 7, kErrCuda = 100;
+
+void set_error(int code, const std::string &msg);
+int last_error_code();
+const char *last_error_msg();
+
+struct ChannelHeader {              // pipeline.rs:123-134
+    uint32_t compressed_len = 0;
+    int32_t quant_step = 1;
+    int32_t quant_dead_zone = 1;
+    uint32_t num_symbols = 0;
+    uint32_t histogram[256] = {0};
+};
+constexpr size_t kChannelHeaderBytes = 1040;  // pipeline.rs:137
+constexpr size_t kFixedHeaderBytes = 18;      // pipeline.rs:148
+
+struct Chunk {                      // pipeline.rs:172-185
+    uint32_t width = 0, height = 0, frames = 0;
+    uint8_t wavelet = 0;
+    ChannelHeader ch[3];
+    std::vector<uint8_t> data;      // concatenated rANS streams Y | Co | Cg
+    std::vector<uint8_t> to_bytes() const;                                   // pipeline.rs:200-226
+    static int from_bytes(const uint8_t *data, size_t len, Chunk &out);      // pipeline.rs:235-313
+};
+
+struct Dims {
+    uint32_t w = 0, h = 0, f = 0;   // as given
+    uint32_t pw = 0, ph = 0, pf = 0;  // padded to even (pipeline.rs:437-439)
+    uint64_t n_pixels = 0, padded = 0;
+};
+// pipeline.rs:67-71 checked_pixel_count + padding; returns kErrOverflow like the reference
+int make_dims(uint32_t w, uint32_t h, uint32_t f, Dims &d);
+int quality_to_step(uint8_t quality);   // pipeline.rs:456-457
+
+struct EngineTimings { float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+
+class Engine {
+public:
+    // payload_cap_per_stream == 0 -> worst case 2N+4 bytes (rANS emits at most 2 bytes per symbol)
+    Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap_per_stream, cudaStream_t user_stream,
+           bool own_stream);
+    ~Engine();
+    bool ok() const { return ok_; }
+    const Dims &dims() const { return d_; }
+    uint32_t cap_chunks() const { return cap_; }
+    uint64_t device_bytes() const { return dev_bytes_; }
+    cudaStream_t stream() const { return st_; }
+
+    // Device-resident encode of n chunks (n <= cap).  d_rgb[i] are device pointers.
+    // coef_dump: optional device i32 [3][N] for chunk 0 (parity tests).
+    int encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const *d_rgb, uint32_t n,
+                      int32_t *d_coef_dump);
+    // Fill a Chunk (headers + payload copied to the host) from the last encode_device.
+    int fetch_chunk(uint32_t i, Chunk &out);
+    // Decode the payloads the last encode_device left on the device.
+    int decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n);
+    // Upload n host chunks (headers + payload) and decode them into device buffers d_rgb_out[i].
+    int decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out);
+
+    // staging buffers for host-pointer entry points
+    uint8_t *rgb_stage(uint32_t slot);          // device buffer of 3*n_pixels bytes, slot in [0, n_stage)
+    uint32_t n_stage() const { return (uint32_t)rgb_stage_.size(); }
+    const uint8_t *symbols_dev(uint32_t chunk) const { return d_symbols_ + (size_t)chunk * 3 * d_.padded; }
+    EngineTimings timings;
+    uint8_t last_wavelet = 0;
+    int last_step = 1;
+    uint32_t last_n = 0;
+
+private:
+    int run_rans_encode(uint32_t n);
+    Dims d_;
+    uint32_t cap_ = 0;
+    uint64_t pay_cap_ = 0;
+    cudaStream_t st_ = nullptr;
+    bool own_stream_ = false, ok_ = false;
+    uint64_t dev_bytes_ = 0;
+    // device
+    void *d_scratch_ = nullptr;       // i16 planes (encode) / i32 coefficients (decode): 4 B * 3 * f*ph*pw
+    uint8_t *d_symbols_ = nullptr;    // [cap][3][N]
+    unsigned *d_hist_ = nullptr;      // [cap][3][256]
+    EncSym *d_enc_ = nullptr;         // [cap*3][256]
+    uint32_t *d_dec_lut_ = nullptr;   // [cap*3][4096]
+    DecAux *d_aux_ = nullptr;         // [cap*3]
+    uint8_t *d_payload_ = nullptr;    // [cap*3][pay_cap]
+    RansEncJob *d_enc_jobs_ = nullptr;
+    RansDecJob *d_dec_jobs_ = nullptr;
+    unsigned long long *d_results_ = nullptr;  // [cap*3][2]
+    std::vector<uint8_t *> rgb_stage_;
+    std::vector<uint8_t *> overflow_bufs_;     // per stream, full-size retry buffers (rare)
+    // pinned host mirrors
+    unsigned long long *h_results_ = nullptr;
+    unsigned *h_hist_ = nullptr;
+    RansEncJob *h_enc_jobs_ = nullptr;
+    RansDecJob *h_dec_jobs_ = nullptr;
+    std::vector<uint64_t> stream_off_;         // offset of stream s inside d_payload_ (or overflow buf)
+    std::vector<uint64_t> stream_len_;
+    std::vector<uint8_t *> stream_base_;
+    cudaEvent_t ev_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// Pool of single-chunk engines behind the reference-ABI entry points (alice_codec_encode / _decode).
+Engine *acquire_engine(const Dims &d);
+void release_engine(Engine *e);
+bool cuda_ready();   // a device is present and usable; sets the CUDA error otherwise
+
+}  // namespace alice

@@ -1,0 +1,321 @@
+// k_forward.cu — encode front-end: RGB u8 -> three u8 symbol planes + three histograms.
+//
+// Replaces, for one chunk (reference file:line):
+//   rgb_bytes_to_ycocg_r            src/color.rs:199-235
+//   pad_channel_to_i32              src/pipeline.rs:77-114 (replicate last col/row/frame)
+//   Wavelet3D::forward              src/wavelet.rs:392-438 (x, then y per frame, then t)
+//   Quantizer::quantize_buffer      src/quant.rs:89-128   (dead zone = step)
+//   to_symbols                      src/quant.rs:547-563  (zig-zag, `as u8` wrap)
+//   build_histogram                 src/quant.rs:594-600
+//
+// Two kernels:
+//   k_fwd_xy        one warp marches one 30*M-pair-wide column strip of one frame down y.
+//                   Each lane owns M horizontal pairs (2M pixels): colour transform and the
+//                   x lifting stay in registers (neighbour values by warp shuffle, lanes 0/31
+//                   are halo lanes); the y lifting is a streaming FwdLift per owned column.
+//                   Output: i16 planes [3][f][ph][pw], de-interleaved in x and y.
+//                   i16 is exact: |coef| <= 7043 after x and y for u8 input.
+//   k_fwd_t_quant   one thread per VEC horizontally adjacent coefficients streams the
+//                   temporal line (padded frames re-read frame f-1), then quantises, maps to
+//                   symbols, stores u8 and histograms through shared-memory atomics.
+// All arithmetic is 32-bit: for u8 input every product (a+b)*c stays below 2^31.
+#include "kernels.h"
+#include "lifting.cuh"
+
+namespace alice {
+
+// ------------------------------------------------------------------------------ k_fwd_xy
+template <int M> struct RowPx { int r[2 * M], g[2 * M], b[2 * M]; };
+
+template <int M>
+ALICE_D void load_row_rgb(const uint8_t *__restrict__ row, int x0, int w, bool vec_ok, RowPx<M> &px) {
+    constexpr int PXL = 2 * M;
+    if (vec_ok && x0 >= 0 && x0 + PXL <= w) {
+        static_assert((PXL * 3) % 4 == 0, "PXL*3 must be a multiple of 4");
+        constexpr int NW = PXL * 3 / 4;
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * 3);
+        uint32_t wd[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) wd[i] = __ldg(p + i);
+#pragma unroll
+        for (int i = 0; i < PXL; i++) {
+            px.r[i] = (wd[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 0xff;
+            px.g[i] = (wd[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 0xff;
+            px.b[i] = (wd[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 0xff;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PXL; i++) {
+            int x = x0 + i;
+            x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);  // replicate-pad (pipeline.rs:95-98)
+            const uint8_t *p = row + (size_t)x * 3;
+            px.r[i] = __ldg(p);
+            px.g[i] = __ldg(p + 1);
+            px.b[i] = __ldg(p + 2);
+        }
+    }
+}
+
+template <int M>
+ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, int limit, bool lane_ok) {
+    // M consecutive coefficients at columns xp .. xp+M-1, valid while column < limit.
+    if (!lane_ok || xp < 0) return;
+    if (M == 2 && xp + 2 <= limit && ((reinterpret_cast<uintptr_t>(dst + xp) & 3) == 0)) {
+        uint32_t pk = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+        *reinterpret_cast<uint32_t *>(dst + xp) = pk;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++)
+        if (xp + i < limit) dst[xp + i] = (int16_t)v[i];
+}
+
+template <int WT, int M>
+__global__ void ALICE_LAUNCH_BOUNDS(128, 3)
+k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, int h, int f, int pw, int ph,
+         int n_strips, int n_segs, int seg_pairs, int vec_ok) {
+    constexpr int NST = WaveletTraits<WT>::NST;
+    constexpr int PXL = 2 * M;
+    constexpr int VPAIRS = 30 * M;
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)n_strips * n_segs * f;
+    if (warp_g >= n_warps) return;  // warp-uniform exit; the kernel has no block-level barrier
+    const int sx = (int)(warp_g % n_strips);
+    const int sg = (int)((warp_g / n_strips) % n_segs);
+    const int t = (int)(warp_g / ((long long)n_strips * n_segs));
+    const int halfx = pw >> 1, halfy = ph >> 1;
+    const int p0 = sx * VPAIRS - M + lane * M;
+    const int x0 = 2 * p0;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const int i0 = sg * seg_pairs;
+    const int i1 = min(halfy, i0 + seg_pairs);
+    const int js = max(0, i0 - NST);
+    const int je = min(halfy, i1 + NST);
+
+    FwdLift<WT, false> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
+    const uint8_t *frame = rgb + (size_t)t * w * h * 3;
+    const size_t plane_sz = (size_t)f * ph * pw;
+    int16_t *out_t = planes + (size_t)t * ph * pw;
+
+    auto emit = [&](int jo, const int (&lo)[3][PXL], const int (&hi)[3][PXL]) {
+        if (jo < i0 || jo >= i1) return;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int16_t *row_lo = out_t + c * plane_sz + (size_t)jo * pw;
+            int16_t *row_hi = out_t + c * plane_sz + (size_t)(halfy + jo) * pw;
+            store_group_i16<M>(row_lo, &lo[c][0], p0, halfx, lane_ok);
+            store_group_i16<M>(row_lo + halfx, &lo[c][M], p0, halfx, lane_ok);
+            store_group_i16<M>(row_hi, &hi[c][0], p0, halfx, lane_ok);
+            store_group_i16<M>(row_hi + halfx, &hi[c][M], p0, halfx, lane_ok);
+        }
+    };
+
+    int k = 0;
+    for (int j = js; j < je; j++, k++) {
+        int v[2][3][PXL];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int y = min(2 * j + r, h - 1);  // replicate-pad the extra row (pipeline.rs:100-105)
+            RowPx<M> px;
+            load_row_rgb<M>(frame + (size_t)y * w * 3, x0, w, vec_ok != 0, px);
+            int e[3][M], o[3][M];
+#pragma unroll
+            for (int i = 0; i < PXL; i++) {
+                // color.rs:221-232 (values fit i16, so i32 arithmetic is identical)
+                int co = px.r[i] - px.b[i];
+                int tt = px.b[i] + (co >> 1);
+                int cg = px.g[i] - tt;
+                int yy = tt + (cg >> 1);
+                if (i & 1) { o[0][i >> 1] = yy; o[1][i >> 1] = co; o[2][i >> 1] = cg; }
+                else       { e[0][i >> 1] = yy; e[1][i >> 1] = co; e[2][i >> 1] = cg; }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                fwd_lanes<WT, false, M>(e[c], o[c], p0, halfx);
+#pragma unroll
+                for (int i = 0; i < M; i++) { v[r][c][i] = e[c][i]; v[r][c][M + i] = o[c][i]; }
+            }
+        }
+        int lo[3][PXL], hi[3][PXL];
+        bool has = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) has = L[c][i].push(v[0][c][i], v[1][c][i], k, j, lo[c][i], hi[c][i]);
+        if (has) emit(j - NST, lo, hi);
+    }
+    if (je == halfy) {
+#pragma unroll
+        for (int which = 0; which < NST; which++) {
+            int lo[3][PXL], hi[3][PXL];
+            bool has = false;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int i = 0; i < PXL; i++) has = L[c][i].flush(k, which, halfy, lo[c][i], hi[c][i]);
+            if (has) emit(halfy - NST + which, lo, hi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- k_fwd_t_quant
+struct QuantDev {
+    int step, dz, half_dz;
+    uint32_t magic;  // ceil(2^32 / step) for step >= 2
+};
+
+ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
+    // Quantizer::quantize (quant.rs:89-97) with step >= 1, then to_symbols (quant.rs:555-560).
+    uint32_t a = (uint32_t)(v < 0 ? -v : v);
+    if ((int)a < q.dz) return 0;
+    uint32_t n = a - (uint32_t)q.half_dz;
+    uint32_t qa = q.step == 1 ? n : __umulhi(n, q.magic);  // exact: n < 2^26, step <= 64
+    if (qa == 0) return 0;
+    return (v > 0 ? 2 * qa - 1 : 2 * qa) & 0xff;
+}
+
+template <int WT, int VEC>
+__global__ void ALICE_LAUNCH_BOUNDS(256, 4)
+k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
+              int pw, int ph, int f, int pf, QuantDev q, int32_t *__restrict__ coef_dump) {
+    constexpr int NST = WaveletTraits<WT>::NST;
+    __shared__ unsigned sh_hist[256];
+    const int c = blockIdx.z;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+
+    const int halft = pf >> 1;
+    const size_t frame_sz = (size_t)ph * pw;
+    const int16_t *src = planes + (size_t)c * f * frame_sz;
+    uint8_t *dst = symbols + (size_t)c * pf * frame_sz;
+    const long long n_items = (long long)(frame_sz / VEC);
+    unsigned zeros = 0;
+
+    auto emit = [&](size_t off, int jo, const int (&lo)[VEC], const int (&hi)[VEC]) {
+        uint32_t pl = 0, phh = 0;
+#pragma unroll
+        for (int i = 0; i < VEC; i++) {
+            uint32_t sl = quant_symbol(lo[i], q), sh = quant_symbol(hi[i], q);
+            pl |= sl << (8 * i);
+            phh |= sh << (8 * i);
+            if (sl) atomicAdd(&sh_hist[sl], 1u); else zeros++;
+            if (sh) atomicAdd(&sh_hist[sh], 1u); else zeros++;
+        }
+        if (coef_dump) {  // parity-test stage dump of the 3-D coefficients (null in production)
+            int32_t *cd = coef_dump + (size_t)c * pf * frame_sz;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                cd[(size_t)jo * frame_sz + off + i] = lo[i];
+                cd[(size_t)(halft + jo) * frame_sz + off + i] = hi[i];
+            }
+        }
+        uint8_t *pl_dst = dst + (size_t)jo * frame_sz + off;
+        uint8_t *ph_dst = dst + (size_t)(halft + jo) * frame_sz + off;
+        if (VEC == 4) {
+            *reinterpret_cast<uint32_t *>(pl_dst) = pl;
+            *reinterpret_cast<uint32_t *>(ph_dst) = phh;
+        } else {
+            *reinterpret_cast<uint16_t *>(pl_dst) = (uint16_t)pl;
+            *reinterpret_cast<uint16_t *>(ph_dst) = (uint16_t)phh;
+        }
+    };
+
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
+         item += (long long)gridDim.x * blockDim.x) {
+        const size_t off = (size_t)item * VEC;
+        FwdLift<WT, false> L[VEC];
+        int k = 0;
+        for (int j = 0; j < halft; j++, k++) {
+            const int t0 = min(2 * j, f - 1), t1 = min(2 * j + 1, f - 1);  // pipeline.rs:107-112
+            int e[VEC], o[VEC];
+            if (VEC == 4) {
+                uint2 a = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t0 * frame_sz + off));
+                uint2 b = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t1 * frame_sz + off));
+                e[0] = (int16_t)(a.x & 0xffff); e[1] = (int)a.x >> 16;
+                o[0] = (int16_t)(b.x & 0xffff); o[1] = (int)b.x >> 16;
+                if (VEC > 2) {
+                    e[VEC - 2] = (int16_t)(a.y & 0xffff); e[VEC - 1] = (int)a.y >> 16;
+                    o[VEC - 2] = (int16_t)(b.y & 0xffff); o[VEC - 1] = (int)b.y >> 16;
+                }
+            } else {
+                uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t0 * frame_sz + off));
+                uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t1 * frame_sz + off));
+                e[0] = (int16_t)(a & 0xffff); e[1] = (int)a >> 16;
+                o[0] = (int16_t)(b & 0xffff); o[1] = (int)b >> 16;
+            }
+            int lo[VEC], hi[VEC];
+            bool has = false;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) has = L[i].push(e[i], o[i], k, j, lo[i], hi[i]);
+            if (has) emit(off, j - NST, lo, hi);
+        }
+#pragma unroll
+        for (int which = 0; which < NST; which++) {
+            int lo[VEC], hi[VEC];
+            bool has = false;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) has = L[i].flush(k, which, halft, lo[i], hi[i]);
+            if (has) emit(off, halft - NST + which, lo, hi);
+        }
+    }
+
+    // zero symbols are counted in a register and folded in once per warp
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) zeros += __shfl_xor_sync(kFullMask, zeros, s);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(&sh_hist[0], zeros);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(&hist[c * 256 + i], sh_hist[i]);
+}
+
+// ------------------------------------------------------------------------------ launchers
+template <int WT>
+static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist, int w, int h,
+                       int f, int pw, int ph, int pf, int step, int32_t *d_coef_dump, cudaStream_t st) {
+    constexpr int M = 2;
+    const int halfx = pw / 2, halfy = ph / 2;
+    const int n_strips = (halfx + 30 * M - 1) / (30 * M);
+    // enough warps to fill the machine: aim for >= 148*24 warps, segments of >= 16 row pairs
+    long long base_warps = (long long)n_strips * f;
+    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * 24 + base_warps - 1) / base_warps),
+                                          std::max(1, halfy / 16));
+    int seg_pairs = (halfy + n_segs - 1) / n_segs;
+    n_segs = (halfy + seg_pairs - 1) / seg_pairs;
+    const long long n_warps = (long long)n_strips * n_segs * f;
+    const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
+    const int warps_per_block = 4;
+    dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
+    auto kxy = k_fwd_xy<WT, M>;
+    ALICE_LAUNCH(kxy, grid, dim3(32 * warps_per_block), 0, st, d_rgb, d_planes, w, h, f, pw, ph, n_strips, n_segs,
+                 seg_pairs, vec_ok);
+
+    QuantDev q;
+    q.step = step;
+    q.dz = step;
+    q.half_dz = step / 2;
+    q.magic = step >= 2 ? (uint32_t)((((uint64_t)1 << 32) + step - 1) / step) : 0;
+    const size_t frame_sz = (size_t)pw * ph;
+    if (pw % 4 == 0) {
+        long long items = frame_sz / 4;
+        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        auto kt = k_fwd_t_quant<WT, 4>;
+        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
+    } else {
+        long long items = frame_sz / 2;
+        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        auto kt = k_fwd_t_quant<WT, 2>;
+        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
+    }
+}
+
+void forward_frontend(int wavelet, const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist,
+                      int w, int h, int f, int pw, int ph, int pf, int step, int32_t *d_coef_dump, cudaStream_t st) {
+    switch (wavelet) {
+    case WT_CDF53: launch_fwd<WT_CDF53>(d_rgb, d_planes, d_symbols, d_hist, w, h, f, pw, ph, pf, step, d_coef_dump, st); break;
+    case WT_CDF97: launch_fwd<WT_CDF97>(d_rgb, d_planes, d_symbols, d_hist, w, h, f, pw, ph, pf, step, d_coef_dump, st); break;
+    default:       launch_fwd<WT_HAAR>(d_rgb, d_planes, d_symbols, d_hist, w, h, f, pw, ph, pf, step, d_coef_dump, st); break;
+    }
+}
+
+}  // namespace alice

@@ -1,0 +1,267 @@
+// k_inverse.cu — decode back-end: three u8 symbol planes -> interleaved RGB u8.
+//
+// Replaces, for one chunk (reference file:line):
+//   from_symbols                    src/quant.rs:572-590
+//   Quantizer::dequantize_buffer    src/quant.rs:104-110, 135-146 (q * step, wrapping)
+//   Wavelet3D::inverse              src/wavelet.rs:441-484 (t, then per frame y, then x)
+//   crop + `as i16`                 src/pipeline.rs:602-611
+//   ycocg_r_to_rgb_bytes            src/color.rs:245-276 (i16 wrapping, clamp to u8)
+//
+// The decoder must reproduce the reference for ANY header (arbitrary quant_step) and any
+// symbol plane — including the garbage the reference decodes from its own malformed
+// frequency tables — so everything here is the reference's wrapping i32
+// arithmetic with the i64 lifting product (WIDE=true), and the t->y hand-off is an i32 volume.
+//
+//   k_inv_t     one thread per VEC adjacent coefficients: symbols -> coefficient, streaming
+//               inverse temporal lifting, writes frames t < f of i32 [3][f][ph][pw].
+//   k_inv_yx    mirror of k_fwd_xy: one warp per column strip marching down y; streaming
+//               inverse y lifting per owned column, lane-parallel inverse x lifting with
+//               shuffles, then crop, i16 truncation, inverse colour transform and RGB store.
+#include "kernels.h"
+#include "lifting.cuh"
+
+namespace alice {
+
+ALICE_D int sym_to_coef(uint32_t s, int step) {
+    // quant.rs:580-588 then quant.rs:104-110
+    int q = (s == 0) ? 0 : ((s & 1) ? (int)((s + 1) >> 1) : -(int)(s >> 1));
+    return (int)((unsigned)q * (unsigned)step);
+}
+
+template <int WT, int VEC>
+__global__ void ALICE_LAUNCH_BOUNDS(256, 4)
+k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw, int ph, int f, int pf, int step0,
+        int step1, int step2) {
+    constexpr int NST = WaveletTraits<WT>::NST;
+    const int c = blockIdx.z;
+    const int step = c == 0 ? step0 : (c == 1 ? step1 : step2);
+    const int halft = pf >> 1;
+    const size_t frame_sz = (size_t)ph * pw;
+    const uint8_t *src = symbols + (size_t)c * pf * frame_sz;
+    int32_t *dst = coef + (size_t)c * f * frame_sz;
+    const long long n_items = (long long)(frame_sz / VEC);
+
+    auto emit = [&](size_t off, int jo, const int (&ev)[VEC], const int (&od)[VEC]) {
+        const int t0 = 2 * jo, t1 = 2 * jo + 1;
+        if (t0 < f) {
+            int32_t *p = dst + (size_t)t0 * frame_sz + off;
+            if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(ev[0], ev[1], ev[VEC - 2], ev[VEC - 1]);
+            else *reinterpret_cast<int2 *>(p) = make_int2(ev[0], ev[1]);
+        }
+        if (t1 < f) {
+            int32_t *p = dst + (size_t)t1 * frame_sz + off;
+            if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(od[0], od[1], od[VEC - 2], od[VEC - 1]);
+            else *reinterpret_cast<int2 *>(p) = make_int2(od[0], od[1]);
+        }
+    };
+
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
+         item += (long long)gridDim.x * blockDim.x) {
+        const size_t off = (size_t)item * VEC;
+        InvLift<WT, true> L[VEC];
+        int k = 0;
+        for (int j = 0; j < halft; j++, k++) {
+            uint32_t a, b;
+            if (VEC == 4) {
+                a = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)j * frame_sz + off));
+                b = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(halft + j) * frame_sz + off));
+            } else {
+                a = __ldg(reinterpret_cast<const uint16_t *>(src + (size_t)j * frame_sz + off));
+                b = __ldg(reinterpret_cast<const uint16_t *>(src + (size_t)(halft + j) * frame_sz + off));
+            }
+            int ev[VEC], od[VEC];
+            bool has = false;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                int lo = sym_to_coef((a >> (8 * i)) & 0xff, step);
+                int hi = sym_to_coef((b >> (8 * i)) & 0xff, step);
+                has = L[i].push(lo, hi, k, j, ev[i], od[i]);
+            }
+            if (has) emit(off, j - NST, ev, od);
+        }
+#pragma unroll
+        for (int which = 0; which < NST; which++) {
+            int ev[VEC], od[VEC];
+            bool has = false;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) has = L[i].flush(k, which, halft, ev[i], od[i]);
+            if (has) emit(off, halft - NST + which, ev, od);
+        }
+    }
+}
+
+template <int M>
+ALICE_D void load_group_i32(const int32_t *__restrict__ row, int xp, int limit, int *v) {
+    if (xp >= 0 && M == 2 && xp + 2 <= limit && ((reinterpret_cast<uintptr_t>(row + xp) & 7) == 0)) {
+        int2 t = __ldg(reinterpret_cast<const int2 *>(row + xp));
+        v[0] = t.x;
+        v[1] = t.y;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        int x = xp + i;
+        v[i] = (x >= 0 && x < limit) ? __ldg(row + x) : 0;
+    }
+}
+
+ALICE_D uint32_t clamp_u8(int16_t v) { return v < 0 ? 0u : (v > 255 ? 255u : (uint32_t)v); }
+
+template <int WT, int M>
+__global__ void ALICE_LAUNCH_BOUNDS(128, 3)
+k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int h, int f, int pw, int ph,
+         int n_strips, int n_segs, int seg_pairs, int vec_ok) {
+    constexpr int NST = WaveletTraits<WT>::NST;
+    constexpr int PXL = 2 * M;
+    constexpr int VPAIRS = 30 * M;
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)n_strips * n_segs * f;
+    if (warp_g >= n_warps) return;
+    const int sx = (int)(warp_g % n_strips);
+    const int sg = (int)((warp_g / n_strips) % n_segs);
+    const int t = (int)(warp_g / ((long long)n_strips * n_segs));
+    const int halfx = pw >> 1, halfy = ph >> 1;
+    const int p0 = sx * VPAIRS - M + lane * M;
+    const int x0 = 2 * p0;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const int i0 = sg * seg_pairs;
+    const int i1 = min(halfy, i0 + seg_pairs);
+    const int js = max(0, i0 - NST);
+    const int je = min(halfy, i1 + NST);
+
+    InvLift<WT, true> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
+    const size_t plane_sz = (size_t)f * ph * pw;
+    const int32_t *in_t = coef + (size_t)t * ph * pw;
+    uint8_t *frame = rgb + (size_t)t * w * h * 3;
+
+    // one reconstructed image row y from its x-subband values (all lanes take part in the shuffles)
+    auto emit_row = [&](int y, bool active, int (&val)[3][PXL]) {
+        int px[3][PXL];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int e[M], o[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) { e[i] = val[c][i]; o[i] = val[c][M + i]; }
+            inv_lanes<WT, true, M>(e, o, p0, halfx);
+#pragma unroll
+            for (int i = 0; i < M; i++) { px[c][2 * i] = e[i]; px[c][2 * i + 1] = o[i]; }
+        }
+        if (!active || !lane_ok || y >= h || x0 < 0 || x0 >= w) return;
+        uint32_t bytes[PXL * 3];
+#pragma unroll
+        for (int i = 0; i < PXL; i++) {
+            // pipeline.rs:608 `as i16`, then color.rs:266-273 in wrapping i16
+            int16_t yy = (int16_t)px[0][i], co = (int16_t)px[1][i], cg = (int16_t)px[2][i];
+            int16_t tt = (int16_t)(yy - (cg >> 1));
+            int16_t g = (int16_t)(cg + tt);
+            int16_t b = (int16_t)(tt - (co >> 1));
+            int16_t r = (int16_t)(co + b);
+            bytes[3 * i] = clamp_u8(r);
+            bytes[3 * i + 1] = clamp_u8(g);
+            bytes[3 * i + 2] = clamp_u8(b);
+        }
+        uint8_t *dst = frame + ((size_t)y * w + x0) * 3;
+        if (vec_ok && x0 + PXL <= w) {
+            constexpr int NW = PXL * 3 / 4;
+#pragma unroll
+            for (int q = 0; q < NW; q++)
+                reinterpret_cast<uint32_t *>(dst)[q] =
+                    bytes[4 * q] | (bytes[4 * q + 1] << 8) | (bytes[4 * q + 2] << 16) | (bytes[4 * q + 3] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PXL; i++)
+                if (x0 + i < w) {
+                    dst[3 * i] = (uint8_t)bytes[3 * i];
+                    dst[3 * i + 1] = (uint8_t)bytes[3 * i + 1];
+                    dst[3 * i + 2] = (uint8_t)bytes[3 * i + 2];
+                }
+        }
+    };
+
+    int k = 0;
+    for (int j = js; j < je; j++, k++) {
+        int ev[3][PXL], od[3][PXL];
+        bool has = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int32_t *row_lo = in_t + c * plane_sz + (size_t)j * pw;
+            const int32_t *row_hi = in_t + c * plane_sz + (size_t)(halfy + j) * pw;
+            int lo[PXL], hi[PXL];
+            load_group_i32<M>(row_lo, p0, halfx, &lo[0]);
+            load_group_i32<M>(row_lo + halfx, p0, halfx, &lo[M]);
+            load_group_i32<M>(row_hi, p0, halfx, &hi[0]);
+            load_group_i32<M>(row_hi + halfx, p0, halfx, &hi[M]);
+#pragma unroll
+            for (int i = 0; i < PXL; i++) has = L[c][i].push(lo[i], hi[i], k, j, ev[c][i], od[c][i]);
+        }
+        if (has) {
+            const int jo = j - NST;
+            const bool active = jo >= i0 && jo < i1;
+            emit_row(2 * jo, active, ev);
+            emit_row(2 * jo + 1, active, od);
+        }
+    }
+    if (je == halfy) {
+#pragma unroll
+        for (int which = 0; which < NST; which++) {
+            int ev[3][PXL], od[3][PXL];
+            bool has = false;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int i = 0; i < PXL; i++) has = L[c][i].flush(k, which, halfy, ev[c][i], od[c][i]);
+            if (has) {
+                const int jo = halfy - NST + which;
+                const bool active = jo >= i0 && jo < i1;
+                emit_row(2 * jo, active, ev);
+                emit_row(2 * jo + 1, active, od);
+            }
+        }
+    }
+}
+
+template <int WT>
+static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f, int pw, int ph,
+                       int pf, const int steps[3], cudaStream_t st) {
+    const size_t frame_sz = (size_t)pw * ph;
+    if (pw % 4 == 0) {
+        long long items = frame_sz / 4;
+        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        auto kt = k_inv_t<WT, 4>;
+        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1],
+                     steps[2]);
+    } else {
+        long long items = frame_sz / 2;
+        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        auto kt = k_inv_t<WT, 2>;
+        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1],
+                     steps[2]);
+    }
+    constexpr int M = 2;
+    const int halfx = pw / 2, halfy = ph / 2;
+    const int n_strips = (halfx + 30 * M - 1) / (30 * M);
+    long long base_warps = (long long)n_strips * f;
+    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * 24 + base_warps - 1) / base_warps),
+                                          std::max(1, halfy / 16));
+    int seg_pairs = (halfy + n_segs - 1) / n_segs;
+    n_segs = (halfy + seg_pairs - 1) / seg_pairs;
+    const long long n_warps = (long long)n_strips * n_segs * f;
+    const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
+    const int warps_per_block = 4;
+    dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
+    auto kyx = k_inv_yx<WT, M>;
+    ALICE_LAUNCH(kyx, grid, dim3(32 * warps_per_block), 0, st, d_coef, d_rgb, w, h, f, pw, ph, n_strips, n_segs,
+                 seg_pairs, vec_ok);
+}
+
+void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f,
+                     int pw, int ph, int pf, const int steps[3], cudaStream_t st) {
+    switch (wavelet) {
+    case WT_CDF53: launch_inv<WT_CDF53>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
+    case WT_CDF97: launch_inv<WT_CDF97>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
+    default:       launch_inv<WT_HAAR>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
+    }
+}
+
+}  // namespace alice

@@ -1,0 +1,76 @@
+// kernels.h — host-callable launchers of every CUDA kernel in libalice_codec.
+// All pointers are device pointers unless a name says host; every call is asynchronous on `st`.
+#pragma once
+#include <algorithm>
+
+#include "compat.h"
+
+namespace alice {
+
+// ---- encode front-end / decode back-end (k_forward.cu, k_inverse.cu) -------------------
+// planes: i16 [3][f][ph][pw] scratch; symbols: u8 [3][pf*ph*pw]; hist: u32 [3][256] (zeroed by caller)
+// coef_dump: optional i32 [3][pf*ph*pw] copy of the 3-D wavelet coefficients (parity tests), else null
+void forward_frontend(int wavelet, const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist,
+                      int w, int h, int f, int pw, int ph, int pf, int step, int32_t *d_coef_dump, cudaStream_t st);
+// symbols: u8 [3][pf*ph*pw]; coef: i32 [3][f][ph][pw] scratch; steps[3] = per-channel quant_step from the header
+void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f,
+                     int pw, int ph, int pf, const int steps[3], cudaStream_t st);
+
+// ---- rANS (k_rans.cu) ------------------------------------------------------------------
+struct EncSym {          // one per symbol, 16 bytes
+    uint32_t x_lim;      // renormalise while x > x_lim   (= freq * 2^19 - 1, saturated)
+    uint32_t rcp;        // ceil(2^(32+sh)/freq) - 1
+    uint32_t cmpl;       // 4096 - freq  (mod 2^32)
+    uint32_t packed;     // cum (16) | sh << 16 (8) | slow << 24 | zero_freq << 25
+};
+struct DecAux {          // per stream
+    uint32_t wide_sym;   // symbol whose freq is outside [1, 4096] (only the last symbol can be), or 0xffffffff
+    uint32_t wide_freq;
+    uint32_t pad[2];
+};
+constexpr int kEncTableBytes = 256 * (int)sizeof(EncSym);
+constexpr int kDecLutEntries = 4096;
+
+// hist [n_streams][256] -> enc [n_streams][256], dec_lut [n_streams][4096], aux [n_streams],
+// freq/cum u16 [n_streams][256] (optional, may be null).  n_symbols <= 256 (256 in the pipeline).
+void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *d_enc, uint32_t *d_dec_lut,
+                  DecAux *d_aux, uint16_t *d_freq, uint16_t *d_cum, uint8_t *d_lut8, cudaStream_t st);
+
+struct RansEncJob {      // device-visible description of one stream to encode
+    const uint8_t *symbols;
+    unsigned long long n;
+    uint8_t *out;        // scratch of `cap` bytes; the stream ends at out+cap
+    unsigned long long cap;
+};
+// results[i] = {len, status}: status 0 ok, 1 overflow (cap too small), 2 zero-frequency symbol (reference aborts)
+void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *d_hist, unsigned long long *d_results,
+                 int n_streams, cudaStream_t st);
+struct RansDecJob {
+    const uint8_t *in;
+    unsigned long long len;
+    uint8_t *symbols;
+    unsigned long long n;
+};
+void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
+                 cudaStream_t st);
+
+// ---- generic element-wise / line kernels behind the public stage API (k_generic.cu) -----
+void lift_axis(int32_t *d_data, int32_t *d_tmp, int wavelet, bool inverse, int axis, long long w, long long h,
+               long long d, cudaStream_t st);  // one 1-D transform along `axis` (0=x,1=y,2=t) of every line
+void rgb_to_ycocg(const uint8_t *d_rgb, int16_t *d_y, int16_t *d_co, int16_t *d_cg, size_t n, cudaStream_t st);
+void ycocg_to_rgb(const int16_t *d_y, const int16_t *d_co, const int16_t *d_cg, uint8_t *d_rgb, size_t n,
+                  cudaStream_t st);
+void quantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int step, int dz, int *d_panic, cudaStream_t st);
+void fast_quantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int dz, unsigned long long recip,
+                       unsigned shift, cudaStream_t st);
+void dequantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int step, cudaStream_t st);
+void to_symbols_u8(const int32_t *d_in, uint8_t *d_out, size_t n, cudaStream_t st);
+void from_symbols_i32(const uint8_t *d_in, int32_t *d_out, size_t n, cudaStream_t st);
+void histogram_u8(const uint8_t *d_in, size_t n, unsigned *d_hist256, cudaStream_t st);  // adds into d_hist256
+void sum_i64(const int32_t *d_in, size_t n, long long *d_sum, cudaStream_t st);          // adds into *d_sum
+void variance_seq_f64(const int32_t *d_in, size_t n, double mean, double *d_acc, cudaStream_t st);
+
+// ---- synthetic inputs (k_synth.cu) ---------------------------------
+void synth_rgb(int kind, uint32_t seed, int w, int h, int f, uint8_t *d_rgb, cudaStream_t st);
+
+}  // namespace alice

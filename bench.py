@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, measured on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--chunks B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] — CDF 9/7, q=80, 1920x1080x64 RGB chunks (synthetic G1
+volumes, SURVEY.md Appendix D, one seed per chunk), encode + decode round trip.  One *step* = one pass of the
+hot path over a batch of B independent chunks per GPU:
+    encode : RGB -> YCoCg-R -> 3-D lifting -> quantise -> symbols + histograms -> frequency tables -> 3B rANS lanes
+    decode : tables -> 3B rANS lanes -> dequantise -> inverse lifting -> RGB
+`value`  = frames/s with the RGB inputs already resident in HBM (whole job, all GPUs).
+`e2e`    = the same metric through the C-ABI batch call with HOST buffers (pinned): H2D of every RGB chunk,
+           D2H of the .alc payloads, H2D of the payloads again for decode, D2H of every decoded RGB chunk.
+`roofline` = the encode front-end (the HBM-bound wavelet/quant stage the north-star targets): 6 algorithmic
+           bytes per pixel (3 in + 3 out) / its CUDA-event duration vs the measured HBM peak.
+`cpu_baseline` = the C oracle (a port of the reference's single-threaded CPU path) on this box's host.
+Multi-GPU: chunks are independent, so each rank runs its own batch (weak scaling), no collective on the data
+path; torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, F = 1920, 1080, 64
+QUALITY, WAVELET = 80, "cdf97"
+SEED = 0x5EED0001
+BYTES_PER_PX_ALG = 6.0          # 3 B in + 3 B out per RGB pixel, front-end or back-end
+WORKLOAD = "CDF 9/7 q=80 1920x1080x64 encode+decode (BASELINE.json configs[1])"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.2)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.err or "no samples"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def _oracle_chunk_seconds(frames, seed, quality=QUALITY, wavelet=1):
+    """One encode+decode round trip of a 1920x1080x`frames` G1 volume through the CPU oracle; returns seconds."""
+    import oracle as O
+    rgb = O.generate(O.G1, W, H, frames, seed)
+    t0 = time.perf_counter()
+    alc = O.encode(rgb, W, H, frames, quality, wavelet)
+    out = O.decode(alc)
+    dt = time.perf_counter() - t0
+    assert out.size == rgb.size
+    return dt
+
+
+def cpu_baseline_single(frames=32):
+    dt = _oracle_chunk_seconds(frames, SEED)
+    return {"value": round(frames / dt, 3), "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"one 1920x1080x{frames} G1 volume (half a chunk), CDF 9/7 q=80, encode+decode through the C oracle "
+                      f"(single thread, like the reference); {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path on all host threads (the reference is a Rust crate and no Rust
+    toolchain exists in this image, so this is the C oracle port; the reference is single-threaded, so the threads
+    run independent chunk slices in parallel, one per worker)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import psutil
+    from concurrent.futures import ThreadPoolExecutor
+    frames = args.ref_frames
+    per_worker_gb = 0.020 * frames * 1.1 + 0.3       # rgb + i16 planes + i32 volume + quantised + symbols (+ copies)
+    avail_gb = psutil.virtual_memory().available / 2**30
+    workers = max(1, min(os.cpu_count() or 1, int(avail_gb * 0.6 / per_worker_gb), 256))
+    import oracle as O
+    O.lib()
+    times = []
+    with ThreadPoolExecutor(workers) as ex:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(lambda i: _oracle_chunk_seconds(frames, SEED + i), range(workers)))  # ctypes releases the GIL
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = workers * frames * len(times) / total
+    sample = (f"{workers} worker threads x one 1920x1080x{frames} G1 slice each per step, "
+              f"CDF 9/7 q=80, encode+decode through the C oracle")
+    line = {"impl": "reference", "metric": "1080p encode+decode frames/s", "value": round(value, 3), "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1000 * total / len(times), 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": round(value, 3), "unit": "frames/s", "cores": workers, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=0, help="chunks in flight per GPU (0 = sized from free HBM)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (0 = min(chunks, 24))")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-frames", type=int, default=16)
+    ap.add_argument("--cpu-frames", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--quality", type=int, default=QUALITY)
+    ap.add_argument("--wavelet", default=WAVELET)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3                      # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libalice_codec has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api = pkg.default_api()
+    api.set_device(local)
+    stream = torch.cuda.current_stream()
+
+    n_px = W * H * F
+    rgb_bytes = 3 * n_px
+    free_b, total_b = torch.cuda.mem_get_info()
+    # per chunk in flight: RGB in + RGB out (bench buffers) + symbols (3 B/px) + payload budget (1.5 B/px + 192 KiB)
+    per_chunk = 2 * rgb_bytes + 3 * n_px + int(1.5 * n_px) + 3 * 65536 + 3 * (4096 + 256 * 16 + 1024)
+    fixed = 12 * n_px + (2 << 30)            # 4-byte scratch volume x 3 channels + head-room
+    B = args.chunks or max(1, min(96, int((free_b - fixed) // per_chunk)))
+    d_in = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
+    d_out = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
+    for i, t in enumerate(d_in):
+        api._chk(api.lib.alice_codec_synth_rgb_device(1, SEED + rank * B + i, W, H, F, C.c_void_p(t.data_ptr()),
+                                                      C.c_void_p(stream.cuda_stream)))
+    torch.cuda.synchronize()
+    batch = pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, B, stream=stream.cuda_stream, api=api)
+    in_ptrs = [t.data_ptr() for t in d_in]
+    out_ptrs = [t.data_ptr() for t in d_out]
+
+    def step():
+        batch.encode_device(in_ptrs)
+        batch.decode_device(out_ptrs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(8)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        stage_ms += np.array(batch.timings())
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    sampler.join(timeout=2)
+    stage_ms /= args.steps
+    ms_step = ms_total / args.steps
+    frames_per_step = B * F * world
+    value = frames_per_step / (ms_step / 1000.0)
+
+    # ---- correctness of what was just timed (bit-exactness is part of the metric)
+    bit_exact = None
+    if rank == 0:
+        golden_path = os.path.join(ROOT, "tests", "golden", "fullsize.json")
+        if os.path.exists(golden_path) and (args.quality, args.wavelet) == (QUALITY, WAVELET):
+            import hashlib
+            g = json.load(open(golden_path)).get("cfg2_cdf97_q80_1080p64")
+            if g:
+                alc = batch.get_chunk(0).to_bytes()
+                bit_exact = (hashlib.sha256(alc).hexdigest() == g["sha256_alc"] and
+                             hashlib.sha256(d_out[0].cpu().numpy().tobytes()).hexdigest() == g["sha256_decoded"])
+
+    # ---- roofline of the HBM-bound front-end stage, from the library's own CUDA events on the launch stream
+    peak, peak_src = _peaks()
+    fe_ms, be_ms = float(stage_ms[0]), float(stage_ms[5])
+    alg_bytes = BYTES_PER_PX_ALG * n_px * B
+    achieved = alg_bytes / (fe_ms / 1000.0) / 1e9 if fe_ms > 0 else 0.0
+    n_sym = 3 * n_px * B
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    roofline = {"bound": "hbm", "kernel": "encode front-end: k_fwd_xy + k_fwd_t_quant over the batch",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms": round(fe_ms, 3),
+                "share_of_step": round(fe_ms / ms_step, 5)}
+    stages = {"frontend_ms": round(fe_ms, 3), "tables_enc_ms": round(float(stage_ms[1]), 3),
+              "rans_encode_ms": round(float(stage_ms[2]), 3), "tables_dec_ms": round(float(stage_ms[3]), 3),
+              "rans_decode_ms": round(float(stage_ms[4]), 3), "backend_ms": round(be_ms, 3),
+              "backend_gbs_alg": round(alg_bytes / (be_ms / 1000.0) / 1e9, 1) if be_ms > 0 else None,
+              "rans_lanes": 3 * B,
+              "rans_encode_msym_s_per_lane": round(n_px / (stage_ms[2] / 1000.0) / 1e6, 2) if stage_ms[2] > 0 else None,
+              "rans_decode_msym_s_per_lane": round(n_px / (stage_ms[4] / 1000.0) / 1e6, 2) if stage_ms[4] > 0 else None,
+              "rans_encode_msym_s_per_sm": round(n_sym / (stage_ms[2] / 1000.0) / 1e6 / n_sm, 2) if stage_ms[2] > 0 else None,
+              "rans_decode_msym_s_per_sm": round(n_sym / (stage_ms[4] / 1000.0) / 1e6 / n_sm, 2) if stage_ms[4] > 0 else None}
+
+    # ---- e2e: the same metric through the host-buffer C-ABI call, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Be = args.e2e_chunks or min(B, 24)
+        h_in = [torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory() for _ in range(Be)]
+        h_out = [torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory() for _ in range(Be)]
+        for i in range(Be):
+            h_in[i].copy_(d_in[i])
+        torch.cuda.synchronize()
+        hin_ptrs, hout_ptrs = [t.data_ptr() for t in h_in], [t.data_ptr() for t in h_out]
+        payload = 0
+
+        def e2e_step():
+            nonlocal payload
+            chunks = batch.encode_host(hin_ptrs)            # H2D RGB, kernels, D2H headers + payload
+            payload = sum(c.compressed_size + 3138 for c in chunks)
+            batch.decode_host(chunks, hout_ptrs)            # H2D payload, kernels, D2H RGB
+        e2e_step()                                          # warm-up (pinned staging, engine staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(Be * F * world * args.e2e_steps / dt, 2), "unit": "frames/s",
+               "h2d_bytes_per_step": Be * rgb_bytes + payload, "d2h_bytes_per_step": Be * rgb_bytes + payload,
+               "chunks_per_step_per_gpu": Be, "timed_with": "host wall clock around synchronous C-ABI calls"}
+        del h_in, h_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single(args.cpu_frames)
+
+    if rank == 0:
+        line = {"metric": "1080p encode+decode frames/s", "value": round(value, 2), "unit": "frames/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "chunks_per_gpu_per_step": B, "frames_per_step": frames_per_step,
+                           "input": "G1 tri+hash volumes generated on the device, one seed per chunk",
+                           "l2": "inputs (%.1f GB per step per GPU) are far larger than the 126 MB L2" % (B * rgb_bytes / 1e9),
+                           "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective"},
+                "e2e": e2e, "gpu_launches": args.steps * (4 * B + 4), "roofline": roofline, "stages": stages,
+                "cpu_baseline": cpu, "clocks": sampler.summary(), "bit_exact_vs_oracle_digest": bit_exact}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,280 @@
+"""Parity checks shared by the CPU (SIMT-emulator) and GPU test tiers.
+
+Every function takes an `Api` (one loaded libalice_codec build) and compares it, through the
+C ABI, with the CPU oracle (oracle/alice_oracle.c) on the same seeded inputs.  The bar is
+bit-exact equality at every stage: wavelet coefficients, symbol planes, histograms, rANS
+streams, .alc bytes and decoded RGB (the path is integer/byte work throughout).
+"""
+import hashlib
+
+import numpy as np
+
+import oracle as O
+from __graft_entry__ import load_package
+
+pkg = load_package()
+WV = {0: "cdf53", 1: "cdf97", 2: "haar"}
+
+
+def check_encode_decode(api, kind, w, h, f, quality, wavelet, seed=O.SEED, stages=True):
+    """FrameEncoder::encode -> to_bytes -> from_bytes -> FrameDecoder::decode vs the oracle, stage by stage."""
+    rgb = O.generate(kind, w, h, f, seed)
+    enc = pkg.FrameEncoder(quality, WV[wavelet], api=api)
+    if stages:
+        chunk, coeffs, syms = enc.encode_stages(rgb, w, h, f)
+        ralc, rco, rsy = O.encode(rgb, w, h, f, quality, wavelet, stages=True)
+        for c in range(3):
+            assert np.array_equal(coeffs[c], rco[c]), f"wavelet coefficients differ (channel {c})"
+            assert np.array_equal(syms[c], rsy[c]), f"symbol plane differs (channel {c})"
+            hdr = chunk.channel_header(c)
+            assert np.array_equal(hdr["histogram"], O.build_histogram(rsy[c])), f"histogram differs (channel {c})"
+            assert hdr["quant_step"] == hdr["quant_dead_zone"] == O.quality_to_step(quality)
+    else:
+        chunk = enc.encode(rgb, w, h, f)
+        ralc = O.encode(rgb, w, h, f, quality, wavelet)
+    alc = chunk.to_bytes()
+    assert len(alc) == len(ralc), f".alc length {len(alc)} != oracle {len(ralc)}"
+    assert alc == ralc, ".alc bytes differ"
+    assert (chunk.width, chunk.height, chunk.frames, chunk.wavelet) == (w, h, f, WV[wavelet])
+    back = pkg.EncodedChunk.from_bytes(ralc, api=api)
+    dec = pkg.FrameDecoder(api=api)
+    if stages:
+        out, dsyms = dec.decode_stages(back)
+        rrgb, rdsy = O.decode(ralc, stages=True)
+        for c in range(3):
+            assert np.array_equal(dsyms[c], rdsy[c]), f"decoded symbol plane differs (channel {c})"
+    else:
+        out = dec.decode(back)
+        rrgb = O.decode(ralc)
+    assert out.size == w * h * f * 3
+    assert np.array_equal(out, rrgb), "decoded RGB differs"
+    return alc, out
+
+
+def check_kat(api, row):
+    kind, w, h, f, q, wv, alen, sha_alc, sha_rgb = row
+    alc, out = check_encode_decode(api, kind, w, h, f, q, wv)
+    assert len(alc) == alen
+    assert hashlib.sha256(alc).hexdigest() == sha_alc
+    assert hashlib.sha256(out.tobytes()).hexdigest() == sha_rgb
+
+
+def check_wavelet_api(api, rng, shapes_1d, shapes_2d, shapes_3d, amplitude=1 << 20):
+    for wv in (0, 1, 2):
+        for n in shapes_1d:
+            x = rng.integers(-amplitude, amplitude, n, dtype=np.int64).astype(np.int32)
+            fw = api.wavelet1d(wv, x)
+            assert np.array_equal(fw, O.wavelet1d_forward(wv, x)), (wv, n)
+            assert np.array_equal(api.wavelet1d(wv, fw, inverse=True), O.wavelet1d_inverse(wv, fw)), (wv, n)
+        for (w, h) in shapes_2d:
+            x = rng.integers(-amplitude, amplitude, w * h, dtype=np.int64).astype(np.int32)
+            fw = api.wavelet2d(wv, x, w, h)
+            assert np.array_equal(fw, O.wavelet2d_forward(wv, x, w, h)), (wv, w, h)
+            assert np.array_equal(api.wavelet2d(wv, fw, w, h, inverse=True), O.wavelet2d_inverse(wv, fw, w, h))
+        for (w, h, d) in shapes_3d:
+            x = rng.integers(-amplitude, amplitude, w * h * d, dtype=np.int64).astype(np.int32)
+            fw = api.wavelet3d(wv, x, w, h, d)
+            assert np.array_equal(fw, O.wavelet3d_forward(wv, x, w, h, d)), (wv, w, h, d)
+            assert np.array_equal(api.wavelet3d(wv, fw, w, h, d, inverse=True),
+                                  O.wavelet3d_inverse(wv, fw, w, h, d))
+
+
+def check_wavelet_extremes(api):
+    """i32 wrap-around and the i64 lifting product (wavelet.rs:193-195): full-range inputs."""
+    rng = np.random.default_rng(7)
+    x = rng.integers(-(1 << 31), (1 << 31) - 1, 4096, dtype=np.int64).astype(np.int32)
+    for wv in (0, 1, 2):
+        fw = api.wavelet1d(wv, x)
+        assert np.array_equal(fw, O.wavelet1d_forward(wv, x))
+        assert np.array_equal(api.wavelet1d(wv, fw, inverse=True), O.wavelet1d_inverse(wv, fw))
+
+
+def check_quant_api(api, rng, n=20000):
+    vals = rng.integers(-70000, 70000, n, dtype=np.int64).astype(np.int32)
+    vals[:8] = [0, 1, -1, 2147483647, -2147483647, -2147483648, 127, -128]
+    for step, dz in [(1, 1), (8, 8), (14, 14), (17, 17), (33, 49), (64, 64), (5, 0), (128, 192), (1000, 1500)]:
+        assert np.array_equal(api.quantize_buffer(step, dz, vals), O.quantize_buffer(step, dz, vals)), (step, dz)
+        assert np.array_equal(api.fast_quantize_buffer(step, dz, vals), O.fast_quantize_buffer(step, dz, vals))
+        q = O.quantize_buffer(step, dz, vals)
+        assert np.array_equal(api.dequantize_buffer(step, q), O.dequantize_buffer(step, q))
+    small = np.arange(-10000, 10001, dtype=np.int32)
+    for step in (1, 2, 3, 7, 8, 14, 17, 33, 64, 100, 127, 128):  # quant.rs:1145-1150
+        assert np.array_equal(api.fast_quantize_buffer(step, step, small), api.quantize_buffer(step, step, small))
+    coeffs = rng.integers(-300, 300, n, dtype=np.int64).astype(np.int32)
+    sy = api.to_symbols(coeffs)
+    assert np.array_equal(sy, O.to_symbols(coeffs))                      # incl. the `as u8` wrap (quant.rs:555-560)
+    assert np.array_equal(api.from_symbols(sy), O.from_symbols(sy))
+    assert np.array_equal(api.build_histogram(sy), O.build_histogram(sy))
+    for bad in (0, -5):                                                   # quant.rs:1116-1122
+        try:
+            api.fast_quantize_buffer(bad, bad, [1])
+            raise AssertionError("InvalidQuantStep expected")
+        except pkg.CodecError as e:
+            assert e.kind == "InvalidQuantStep"
+
+
+def check_rdo(api, rng):
+    for q in (0, 10, 50, 75, 90, 100, 200):
+        assert api.rdo_bpp_from_quality(q) == O.rdo_bpp_from_quality(q)
+    for n in (0, 1, 7, 1000, 4097):
+        x = rng.integers(-500, 500, n, dtype=np.int64).astype(np.int32)
+        for sb in range(8):
+            for bpp in (0.1, 1.0, O.rdo_bpp_from_quality(75)):
+                assert api.rdo_compute_quantizer(bpp, x, sb) == O.rdo_compute_quantizer(bpp, x, sb), (n, sb, bpp)
+
+
+def check_colour(api, rng, n=5000):
+    rgb = rng.integers(0, 256, 3 * n, dtype=np.int64).astype(np.uint8)
+    rgb[:12] = [0, 0, 0, 255, 255, 255, 255, 0, 0, 0, 0, 255]
+    y, co, cg = api.rgb_to_ycocg_r(rgb)
+    ry, rco, rcg = O.rgb_bytes_to_ycocg_r(rgb)
+    assert np.array_equal(y, ry) and np.array_equal(co, rco) and np.array_equal(cg, rcg)
+    assert np.array_equal(api.ycocg_r_to_rgb(y, co, cg), rgb)            # color.rs:429-461 exact round trip
+    wild = [rng.integers(-32768, 32768, n, dtype=np.int64).astype(np.int16) for _ in range(3)]
+    assert np.array_equal(api.ycocg_r_to_rgb(*wild), O.ycocg_r_to_rgb_bytes(*wild))   # i16 wrap + clamp
+
+
+def _check_rans(api, sy, hist):
+    hist = np.asarray(hist, np.uint32)
+    t = O.freq_table_from_histogram(hist)
+    cum, freq, lut = api.freq_table_from_histogram(hist)
+    n = hist.size
+    assert np.array_equal(cum, t.cum_np()[:n]) and np.array_equal(freq, t.freq_np()[:n])
+    assert np.array_equal(lut, t.lut_np())
+    try:
+        ref = O.rans_encode(sy, t)
+    except O.OracleError:
+        try:
+            api.rans_encode(sy, hist)
+            raise AssertionError("reference panics (zero frequency); CUDA path must report it")
+        except pkg.CodecError as e:
+            assert e.kind == "ReferencePanic"
+        return
+    got = api.rans_encode(sy, hist)
+    assert got == ref, "rANS stream differs"
+    assert np.array_equal(api.rans_decode(ref, sy.size, hist), O.rans_decode(ref, sy.size, t)), "rANS decode differs"
+    # decoders must also agree on truncated / empty input (rans.rs:341-347, 363-368)
+    for cut in (0, 3, 4, len(ref) // 2):
+        assert np.array_equal(api.rans_decode(ref[:cut], min(sy.size, 300), hist),
+                              O.rans_decode(ref[:cut], min(sy.size, 300), t))
+
+
+def check_rans_api(api, rng, n=6000):
+    # well-formed skewed table, low-numbered symbols (rans.rs:738-787)
+    p = np.array([0.7, 0.1, 0.08, 0.05, 0.04, 0.02, 0.01])
+    sy = rng.choice(7, n, p=p).astype(np.uint8)
+    _check_rans(api, sy, O.build_histogram(sy))
+    # 4-bin histogram (rans.rs:819-830) and a uniform table via an all-zero histogram (rans.rs:158-189)
+    sy4 = rng.integers(0, 4, n).astype(np.uint8)
+    _check_rans(api, sy4, [100, 200, 300, 400])
+    syu = rng.integers(0, 256, n).astype(np.uint8)
+    _check_rans(api, syu, np.zeros(256, np.uint32))
+    _check_rans(api, rng.integers(0, 16, 500).astype(np.uint8), np.zeros(16, np.uint32))
+    # gappy histogram -> malformed table, freq[255] wraps: streams must still be identical
+    sy = (rng.choice(60, n, p=np.r_[0.5, np.full(59, 0.5 / 59)]) * 2 + 1).astype(np.uint8)
+    sy[rng.integers(0, n, n // 4)] = 0
+    _check_rans(api, sy, O.build_histogram(sy))
+    # symbol 255 in use with the wrapped frequency; full-range noise; single dominant symbol; tiny inputs
+    sy = rng.integers(0, 256, n).astype(np.uint8)
+    _check_rans(api, sy, O.build_histogram(sy))
+    sy = np.where(rng.random(n) < 0.97, 0, rng.integers(1, 256, n)).astype(np.uint8)
+    _check_rans(api, sy, O.build_histogram(sy))
+    sy = np.full(n, 100, np.uint8)
+    _check_rans(api, sy, O.build_histogram(sy))
+    for m in (0, 1, 2, 15, 16, 17, 511, 512, 513, 1025):
+        sy = rng.integers(0, 9, m).astype(np.uint8)
+        _check_rans(api, sy, O.build_histogram(rng.integers(0, 9, 64).astype(np.uint8)) if m == 0 else O.build_histogram(sy))
+
+
+def check_errors(api):
+    """Error contract of FrameEncoder::encode / from_bytes / decode (pipeline.rs:384-427, 235-313, 562-579)."""
+    enc = pkg.FrameEncoder(90, "cdf53", api=api)
+    for (n, w, h, f, kind) in [(10, 4, 4, 2, "InvalidBufferSize"), (3, 0, 4, 2, "InvalidBufferSize"),
+                               (0, 4, 4, 2, "InvalidBufferSize"), (12, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, "DimensionOverflow")]:
+        try:
+            enc.encode(np.zeros(n, np.uint8), w, h, f)
+            raise AssertionError(f"{kind} expected")
+        except pkg.CodecError as e:
+            assert e.kind == kind, (e.kind, kind)
+        try:
+            O.encode(np.zeros(n, np.uint8), w, h, f, 90, 0)
+            raise AssertionError("oracle accepted it")
+        except O.OracleError as e:
+            assert O.ERR_NAMES[e.code] == kind
+    # empty chunk (pipeline.rs:391-412): 3138-byte .alc, decodes to nothing
+    ck = enc.encode(np.zeros(0, np.uint8), 0, 0, 0)
+    alc = ck.to_bytes()
+    assert alc == O.encode(np.zeros(0, np.uint8), 0, 0, 0, 90, 0) and len(alc) == 3138
+    assert pkg.FrameDecoder(api=api).decode(pkg.EncodedChunk.from_bytes(alc, api=api)).size == 0
+    good = O.encode(O.generate(O.G0, 4, 4, 2), 4, 4, 2, 90, 0)
+    bad_inputs = [good[:100], b"XLCC" + good[4:], good[:4] + b"\x02" + good[5:], good[:5] + b"\x03" + good[6:],
+                  good[:-1]]
+    for b in bad_inputs:
+        try:
+            pkg.EncodedChunk.from_bytes(b, api=api)
+            raise AssertionError("InvalidBitstream expected")
+        except pkg.CodecError as e:
+            assert e.kind == "InvalidBitstream"
+    assert pkg.EncodedChunk.from_bytes(good + b"junk", api=api).to_bytes() == good     # trailing bytes ignored
+    # num_symbols mismatch is caught by decode, not from_bytes (pipeline.rs:566-570)
+    tampered = bytearray(good)
+    tampered[18 + 12] ^= 1
+    ck = pkg.EncodedChunk.from_bytes(bytes(tampered), api=api)
+    try:
+        pkg.FrameDecoder(api=api).decode(ck)
+        raise AssertionError("InvalidBitstream expected")
+    except pkg.CodecError as e:
+        assert e.kind == "InvalidBitstream"
+
+
+def check_decode_foreign_headers(api, rng):
+    """The decoder takes step/dead-zone/histograms from the header (pipeline.rs:582-595): tamper and compare."""
+    w, h, f = 20, 12, 6
+    alc = bytearray(O.encode(O.generate(O.G1, w, h, f), w, h, f, 80, 1))
+    for c, step in enumerate((3, 1000, -7)):
+        off = 18 + c * 1040 + 4
+        alc[off:off + 4] = int(step).to_bytes(4, "little", signed=True)
+    off = 18 + 1040 + 16                               # Co histogram: shuffle some counts -> other table, garbage symbols
+    hist = np.frombuffer(bytes(alc[off:off + 1024]), np.uint32).copy()
+    hist[:16] = hist[:16][::-1]
+    alc[off:off + 1024] = hist.tobytes()
+    out = pkg.FrameDecoder(api=api).decode(pkg.EncodedChunk.from_bytes(bytes(alc), api=api))
+    assert np.array_equal(out, O.decode(bytes(alc)))
+
+
+def check_reference_abi(api):
+    """The 20 reference symbols used the way a consumer of the reference's cdylib does (ffi.rs tests :325-484)."""
+    L = api.lib
+    abi = pkg.ReferenceAbi(api)
+    assert api.version() == "0.1.2"                                        # ffi.rs:311
+    w, h, f = 16, 10, 4
+    rgb = O.generate(O.G0, w, h, f)
+    alc = abi.encode_to_bytes(rgb, w, h, f, quality=90)
+    assert alc == O.encode(rgb, w, h, f, 90, 0)                            # encoder_create is always CDF 5/3 (ffi.rs:92)
+    assert np.array_equal(abi.decode_from_bytes(alc), O.decode(alc))
+    assert abi.encode_to_bytes(rgb[:-1], w, h, f) is None                  # errors are a null return
+    assert abi.decode_from_bytes(alc[:50]) is None
+    # null safety (ffi.rs:325-484)
+    L.alice_codec_wavelet1d_destroy(None)
+    L.alice_codec_encoder_destroy(None)
+    L.alice_codec_chunk_destroy(None)
+    L.alice_codec_data_free(None, 0)
+    L.alice_codec_string_free(None)
+    assert L.alice_codec_chunk_width(None) == 0 and L.alice_codec_chunk_height(None) == 0
+    assert L.alice_codec_chunk_frames(None) == 0
+    assert L.alice_codec_encode(None, None, 0, 1, 1, 1) is None
+    import ctypes as C
+    n = C.c_uint32()
+    assert L.alice_codec_decode(None, C.byref(n)) is None
+    assert L.alice_codec_chunk_to_bytes(None, C.byref(n)) is None
+    assert L.alice_codec_chunk_from_bytes(None, 0) is None
+    assert L.alice_codec_psnr(None, None, 0) == -1.0
+    a = np.arange(30, dtype=np.uint8)
+    assert api.psnr(a, a) == float("inf")
+    b = a.copy(); b[3] += 9
+    assert abs(api.psnr(a, b) - O.psnr(a, b)) < 1e-12
+    # wavelet1d through the reference handles, incl. len < 2 no-op and odd length (wavelet.rs:133-137, 220-233)
+    for wv in (0, 1, 2):
+        for n_ in (0, 1, 2, 3, 9, 64):
+            x = (np.arange(n_, dtype=np.int32) * 37 - 100) % 251
+            assert np.array_equal(api.wavelet1d(wv, x), O.wavelet1d_forward(wv, x))

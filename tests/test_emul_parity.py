@@ -1,0 +1,60 @@
+"""CPU tier: the CUDA kernel sources compiled against the SIMT emulator (tests/emul/cuda_emul.h, test
+infrastructure) and driven through the same C ABI, compared bit for bit with the oracle.  This debugs kernel
+*logic* where no GPU exists; the -m gpu tier (test_gpu_parity.py) is the parity proof on real hardware."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity
+from ref_vectors import SURVEY_KATS
+
+pkg = parity.pkg
+
+
+@pytest.fixture(scope="module")
+def api():
+    spec = importlib.util.spec_from_file_location("b", os.path.join(os.path.dirname(pkg.__file__), "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    return pkg.Api(b.build_emul())
+
+
+@pytest.mark.parametrize("row", SURVEY_KATS, ids=lambda r: f"G{r[0]}-{r[1]}x{r[2]}x{r[3]}-q{r[4]}-w{r[5]}")
+def test_survey_kats(api, row):
+    parity.check_kat(api, row)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 2, 2), (3, 5, 1), (5, 3, 3), (7, 2, 4), (2, 9, 5), (66, 6, 2),
+                                   (130, 4, 2), (6, 70, 2), (12, 6, 64)])
+@pytest.mark.parametrize("wavelet", [0, 1, 2])
+def test_odd_and_edge_shapes(api, shape, wavelet):
+    w, h, f = shape
+    parity.check_encode_decode(api, O.G1, w, h, f, 80, wavelet)
+
+
+@pytest.mark.parametrize("kind,quality", [(O.G2, 100), (O.G2, 0), (O.G0, 100), (O.G1, 50)])
+def test_noise_and_extreme_quality(api, kind, quality):
+    for wavelet in (0, 1, 2):
+        parity.check_encode_decode(api, kind, 24, 10, 6, quality, wavelet)
+
+
+def test_stage_apis(api):
+    rng = np.random.default_rng(1)
+    parity.check_wavelet_api(api, rng, [2, 3, 8, 9, 31], [(4, 4), (5, 3), (16, 9)], [(4, 4, 4), (5, 3, 2), (8, 6, 3)])
+    parity.check_wavelet_extremes(api)
+    parity.check_quant_api(api, rng, n=3000)
+    parity.check_colour(api, rng, n=1000)
+    parity.check_rdo(api, rng)
+
+
+def test_rans_api(api):
+    parity.check_rans_api(api, np.random.default_rng(2), n=3000)
+
+
+def test_errors_and_abi(api):
+    parity.check_errors(api)
+    parity.check_reference_abi(api)
+    parity.check_decode_foreign_headers(api, np.random.default_rng(3))

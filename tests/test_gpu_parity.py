@@ -1,0 +1,206 @@
+"""GPU tier (-m gpu): the parity tests proper.  The in-tree CUDA library (sm_100a) is driven through its C ABI and
+compared bit for bit with the CPU oracle on the same seeded inputs; BASELINE.json's full sizes are checked
+against committed oracle digests (tests/golden/fullsize.json) and through size-independent properties."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity
+from ref_vectors import SURVEY_KATS
+
+pkg = parity.pkg
+pytestmark = pytest.mark.gpu
+GOLDEN_PATH = os.path.join(os.path.dirname(__file__), "golden", "fullsize.json")
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def api():
+    a = pkg.Api()                      # the product library; raises if it is missing (no fallback)
+    assert a.path.endswith("alice-codec_b200/lib/libalice_codec.so")
+    assert a.device_count() >= 1, "no CUDA device visible to libalice_codec"
+    a.set_device(0)
+    return a
+
+
+@pytest.mark.parametrize("row", SURVEY_KATS, ids=lambda r: f"G{r[0]}-{r[1]}x{r[2]}x{r[3]}-q{r[4]}-w{r[5]}")
+def test_survey_kats(api, row):
+    parity.check_kat(api, row)
+
+
+SHAPES = [(1, 1, 1), (2, 2, 2), (3, 5, 1), (5, 3, 3), (7, 2, 4), (2, 9, 5), (1, 40, 7), (40, 1, 7), (66, 6, 2),
+          (130, 4, 2), (6, 70, 2), (12, 6, 64), (121, 67, 9), (124, 62, 64), (250, 30, 3), (64, 64, 65), (31, 33, 128)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("wavelet", [0, 1, 2])
+def test_odd_and_edge_shapes(api, shape, wavelet):
+    w, h, f = shape
+    parity.check_encode_decode(api, O.G1, w, h, f, 80, wavelet)
+
+
+@pytest.mark.parametrize("kind", [O.G0, O.G1, O.G2])
+@pytest.mark.parametrize("quality", [0, 50, 75, 80, 90, 100])
+def test_every_quality_and_input_kind(api, kind, quality):
+    for wavelet in (0, 1, 2):
+        parity.check_encode_decode(api, kind, 96, 40, 16, quality, wavelet)
+
+
+@pytest.mark.parametrize("cfg", [(90, 0), (80, 1), (75, 2)], ids=["cdf53-q90", "cdf97-q80", "haar-q75"])
+@pytest.mark.parametrize("shape", [(256, 128, 64), (640, 360, 16), (1920, 1080, 2)], ids=lambda s: "x".join(map(str, s)))
+def test_baseline_configs_medium(api, cfg, shape):
+    """BASELINE.json configs 1-3 at sizes the oracle finishes in seconds (full stage-by-stage comparison)."""
+    q, wv = cfg
+    w, h, f = shape
+    parity.check_encode_decode(api, O.G1, w, h, f, q, wv)
+    parity.check_encode_decode(api, O.G2, w // 2, h // 2, f, q, wv)
+
+
+def _fullsize(api, name, want_coeffs):
+    g = json.load(open(GOLDEN_PATH))[name]
+    rgb = O.generate(g["kind"], g["w"], g["h"], g["f"], g["seed"])
+    assert sha(rgb.tobytes()) == g["sha256_rgb_in"]
+    enc = pkg.FrameEncoder(g["quality"], g["wavelet"], api=api)
+    chunk, coeffs, syms = enc.encode_stages(rgb, g["w"], g["h"], g["f"], want_coeffs=want_coeffs)
+    del rgb
+    n = syms.shape[1]
+    for c in range(3):
+        if want_coeffs:
+            assert sha(coeffs[c].tobytes()) == g["sha256_coeffs"][c], f"coefficients differ (channel {c})"
+        assert sha(syms[c].tobytes()) == g["sha256_symbols"][c], f"symbols differ (channel {c})"
+        hdr = chunk.channel_header(c)
+        assert int(hdr["histogram"].sum(dtype=np.uint64)) == n == hdr["num_symbols"]      # property: counts add up
+        assert np.array_equal(hdr["histogram"], np.bincount(syms[c], minlength=256))      # property: hist == symbols
+        assert hdr["compressed_len"] == g["stream_lens"][c]
+    del coeffs
+    alc = chunk.to_bytes()
+    assert len(alc) == g["alc_len"]
+    assert sha(alc[:3138]) == g["sha256_header"]
+    assert sha(alc) == g["sha256_alc"], ".alc differs from the oracle digest"
+    out, dsyms = pkg.FrameDecoder(api=api).decode_stages(pkg.EncodedChunk.from_bytes(alc, api=api))
+    assert sha(out.tobytes()) == g["sha256_decoded"], "decoded RGB differs from the oracle digest"
+    # property: a channel whose used symbols all sit inside [0,4096) of the table must survive the rANS round trip
+    for c in range(3):
+        cum, freq, _ = api.freq_table_from_histogram(chunk.channel_header(c)["histogram"])
+        used = np.nonzero(chunk.channel_header(c)["histogram"])[0]
+        if np.all(cum[used].astype(np.int64) + freq[used] <= 4096):
+            assert np.array_equal(dsyms[c], syms[c]), f"well-formed stream {c} failed its round trip"
+
+
+def test_fullsize_config1_cdf53_q90_1080p64(api):
+    _fullsize(api, "cfg1_cdf53_q90_1080p64", want_coeffs=True)
+
+
+def test_fullsize_config2_cdf97_q80_1080p64(api):
+    _fullsize(api, "cfg2_cdf97_q80_1080p64", want_coeffs=True)
+
+
+def test_fullsize_config3_haar_q75_4k64(api):
+    _fullsize(api, "cfg3_haar_q75_4k64", want_coeffs=False)
+
+
+def test_fullsize_odd_and_noise(api):
+    _fullsize(api, "odd_cdf97_q80_1919x1079x63", want_coeffs=False)
+    _fullsize(api, "noise_cdf53_q90_1080p8", want_coeffs=True)
+
+
+def test_stage_apis(api):
+    rng = np.random.default_rng(1)
+    parity.check_wavelet_api(api, rng, [2, 3, 8, 9, 31, 1000, 1921], [(4, 4), (5, 3), (16, 9), (321, 65)],
+                             [(4, 4, 4), (5, 3, 2), (8, 6, 3), (64, 36, 64), (33, 17, 9)])
+    parity.check_wavelet_extremes(api)
+    parity.check_quant_api(api, rng, n=200000)
+    parity.check_colour(api, rng, n=100000)
+    parity.check_rdo(api, rng)
+
+
+def test_lossless_config4_transform(api):
+    """BASELINE config 4: LosslessEncoder::transform_2d / inverse_2d (lossless.rs:45-54) == Wavelet2D::cdf53 per
+    frame of the Y/Co/Cg planes; symbols (step 1, wrapping), histogram, table, rANS round trip per stream."""
+    w, h, f = 480, 270, 4
+    planes = O.rgb_bytes_to_ycocg_r(O.generate(O.G1, w, h, f))
+    for p in planes:
+        for t in range(f):
+            img = p[t * w * h:(t + 1) * w * h].astype(np.int32)
+            fw = api.wavelet2d(0, img, w, h)
+            assert np.array_equal(fw, O.wavelet2d_forward(0, img, w, h))
+            assert np.array_equal(api.wavelet2d(0, fw, w, h, inverse=True), O.wavelet2d_inverse(0, fw, w, h))
+            if t == 0:
+                sy = api.to_symbols(fw)
+                assert np.array_equal(sy, O.to_symbols(fw))
+                hist = api.build_histogram(sy)
+                table = O.freq_table_from_histogram(hist)
+                stream = api.rans_encode(sy, hist)
+                assert stream == O.rans_encode(sy, table)
+                assert np.array_equal(api.rans_decode(stream, sy.size, hist), O.rans_decode(stream, sy.size, table))
+
+
+def test_rans_api(api):
+    parity.check_rans_api(api, np.random.default_rng(2), n=300000)
+
+
+def test_errors_and_abi(api):
+    parity.check_errors(api)
+    parity.check_reference_abi(api)
+    parity.check_decode_foreign_headers(api, np.random.default_rng(3))
+
+
+def test_batch_api_device_and_host(api):
+    """The throughput path: many chunks of one shape in flight (alice_codec_batch_*), device and host variants."""
+    import torch
+    w, h, f, n = 128, 72, 16, 5
+    for q, wv in [(90, "cdf53"), (80, "cdf97"), (75, "haar")]:
+        batch = pkg.ChunkBatch(q, wv, w, h, f, n, stream=torch.cuda.current_stream().cuda_stream, api=api)
+        rgbs = [O.generate(O.G1 if i != 3 else O.G2, w, h, f, O.SEED + i) for i in range(n)]
+        d_in = [torch.from_numpy(r).cuda() for r in rgbs]
+        d_out = [torch.zeros_like(t) for t in d_in]
+        batch.encode_device([t.data_ptr() for t in d_in])
+        refs = [O.encode(r, w, h, f, q, pkg.WAVELET_NAMES[wv]) for r in rgbs]
+        for i in range(n):
+            assert batch.get_chunk(i).to_bytes() == refs[i], f"chunk {i}"
+        batch.decode_device([t.data_ptr() for t in d_out])
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert np.array_equal(d_out[i].cpu().numpy(), O.decode(refs[i])), f"decoded chunk {i}"
+        # host variant (H2D / D2H inside the call)
+        h_in = [torch.from_numpy(r).pin_memory() for r in rgbs]
+        h_out = [torch.zeros(r.size, dtype=torch.uint8).pin_memory() for r in rgbs]
+        chunks = batch.encode_host([t.data_ptr() for t in h_in])
+        assert [c.to_bytes() for c in chunks] == refs
+        batch.decode_host(chunks, [t.data_ptr() for t in h_out])
+        for i in range(n):
+            assert np.array_equal(h_out[i].numpy(), O.decode(refs[i]))
+        assert len(batch.timings()) == 8 and batch.device_bytes() > 0
+        batch.close()
+
+
+def test_synth_on_device_matches_oracle_generators(api):
+    import ctypes as C
+    import torch
+    for kind in (O.G0, O.G1, O.G2):
+        for (w, h, f) in [(64, 32, 8), (33, 17, 5)]:
+            t = torch.empty(w * h * f * 3, dtype=torch.uint8, device="cuda")
+            api._chk(api.lib.alice_codec_synth_rgb_device(kind, O.SEED, w, h, f, C.c_void_p(t.data_ptr()), None))
+            torch.cuda.synchronize()
+            assert np.array_equal(t.cpu().numpy(), O.generate(kind, w, h, f))
+
+
+def test_determinism_and_idempotence(api):
+    w, h, f = 320, 180, 32
+    rgb = O.generate(O.G1, w, h, f)
+    enc = pkg.FrameEncoder(80, "cdf97", api=api)
+    a = enc.encode(rgb, w, h, f).to_bytes()
+    b = enc.encode(rgb, w, h, f).to_bytes()
+    assert a == b
+    ck = pkg.EncodedChunk.from_bytes(a, api=api)
+    assert pkg.EncodedChunk.from_bytes(ck.to_bytes(), api=api).to_bytes() == a
+    d1 = pkg.FrameDecoder(api=api).decode(ck)
+    d2 = pkg.FrameDecoder(api=api).decode(ck)
+    assert np.array_equal(d1, d2)

@@ -533,7 +533,7 @@ int alice_codec_rans_encode(const uint8_t *symbols, uint64_t n64, const uint32_t
             return kErrPanic;
         }
     if (!cuda_ready()) return kErrCuda;
-    const size_t cap = (2 * n + 4 + 15) / 16 * 16;
+    const size_t cap = rans_enc_worst_case(n);
     DevBuf h, enc, dec, aux, sy, pay, job, res;
     if (!h.alloc(1024) || !enc.alloc(kEncTableBytes) || !dec.alloc(kDecLutEntries * 4) || !aux.alloc(sizeof(DecAux)) ||
         !sy.alloc(n) || !pay.alloc(cap) || !job.alloc(sizeof(RansEncJob)) || !res.alloc(16))
@@ -571,7 +571,7 @@ int alice_codec_rans_decode(const uint8_t *stream, uint64_t len64, const uint32_
     if (!cuda_ready()) return kErrCuda;
     DevBuf h, enc, dec, aux, sy, in, job;
     if (!h.alloc(1024) || !enc.alloc(kEncTableBytes) || !dec.alloc(kDecLutEntries * 4) || !aux.alloc(sizeof(DecAux)) ||
-        !sy.alloc(n) || !in.alloc(len) || !job.alloc(sizeof(RansDecJob)))
+        !sy.alloc(n) || !in.alloc(len + 32) || !job.alloc(sizeof(RansDecJob)))
         return kErrCuda;
     CU_CHECK_RC(cudaMemset(h.p, 0, 1024));
     CU_CHECK_RC(cudaMemcpy(h.p, hist, n_symbols * 4, cudaMemcpyHostToDevice));

@@ -125,7 +125,7 @@ Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStr
     : d_(d), cap_(cap_chunks), own_stream_(own_stream) {
     const size_t N = (size_t)d_.padded;
     const size_t vol = (size_t)d_.f * d_.ph * d_.pw;
-    pay_cap_ = round_up(payload_cap ? (size_t)payload_cap : 2 * N + 4, 16);
+    pay_cap_ = payload_cap ? round_up((size_t)payload_cap, 16) : rans_enc_worst_case(N);
     const size_t S = (size_t)cap_ * 3;
     if (own_stream_) {
         if (cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
@@ -206,7 +206,7 @@ int Engine::run_rans_encode(uint32_t n) {
         }
         if (status & 1) {
             // payload did not fit the per-stream capacity: redo this stream into a worst-case buffer
-            const size_t full = round_up(2 * N + 4, 16);
+            const size_t full = rans_enc_worst_case(N);
             if (!overflow_bufs_[s]) {
                 if (!dev_alloc(overflow_bufs_[s], full, dev_bytes_)) {
                     set_error(kErrCuda, "device memory allocation failed (rANS overflow buffer)");
@@ -344,7 +344,7 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             const size_t len = ck.ch[c].compressed_len;
             uint8_t *dst = d_payload_ + (size_t)s * pay_cap_;
             if (len > pay_cap_) {
-                const size_t full = round_up(std::max(len, 2 * N + 4), 16);
+                const size_t full = std::max(round_up(len, 16), rans_enc_worst_case(N));
                 if (overflow_bufs_[s]) { cudaFree(overflow_bufs_[s]); overflow_bufs_[s] = nullptr; }
                 if (!dev_alloc(overflow_bufs_[s], full, dev_bytes_)) {
                     set_error(kErrCuda, "device memory allocation failed (payload)");

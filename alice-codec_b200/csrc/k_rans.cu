@@ -6,16 +6,26 @@
 //   RansEncoder::{new, encode, encode_symbols, finish}   src/rans.rs:249-308
 //   RansDecoder::{new, init_state, decode, decode_n}     src/rans.rs:330-381
 //
-// rANS is a serial recurrence on a 32-bit state; .alc carries no side information, so a
-// stream cannot be split bit-exactly.  The design therefore (a) keeps ONLY the state
-// recurrence on the critical path — table entries are expanded per symbol into
-// {renorm limit, exact reciprocal, 4096-freq, cum} so that x/freq is one widening multiply
-// and one shift, symbols are fetched 512 at a time by the whole warp and broadcast by
-// shuffle, the decoder pre-loads its next stream byte — and (b) runs every stream of every
-// in-flight chunk in one launch (grid = number of streams) so all SMs carry lanes.
+// rANS is a serial recurrence on a 32-bit state and .alc carries no side information, so a
+// stream cannot be split bit-exactly: throughput comes from (a) the shortest possible
+// dependent chain per symbol and (b) hundreds of streams in flight (grid = streams of all
+// in-flight chunks).  Every thread of the warp executes the same recurrence on the same
+// values (the warp is a scalar engine with a 32-wide memory system): symbols, stream bytes
+// and output are moved 512 at a time by all lanes through shared-memory rings, so the
+// serial code touches only shared memory and registers.
 //
-// Every thread of the warp executes the same recurrence on the same values (the warp is a
-// scalar engine with 32-wide fetch); only lane 0 stores.
+// Encoder step (src/rans.rs:269-285), branch-free for freq in (16, 4096]:
+//     k  = x > freq*2^19 - 1                     (one renormalisation byte at most when freq > 16)
+//     q0 = floor(x / freq) = ((x*rcp + rcp) >> 32) >> sh      exact for x < 2^31 + 2^15
+//     q  = q0 >> 8k        because floor(floor(x / 256) / f) == floor(floor(x / f) / 256)
+//     x' = (x >> 8k) + cum + q * (4096 - freq)   == ((x>>8k) / f << 12) + (x>>8k) % f + cum
+// so the division does not wait for the renormalisation decision.  Symbols with freq <= 16,
+// freq > 4096 (the wrapped last symbol of a malformed table) or freq == 0 take a generic step.
+//
+// Decoder step (src/rans.rs:351-371): symbol 0 owns slots [0, freq0), so the common case
+// needs no table access; other slots read {freq, slot - cum} from a 4096-entry shared table.
+// Stream bytes come from a shared "window" table holding, for every byte position, the next
+// four bytes as one big-endian word, so renormalisation is two predicated funnel shifts.
 #include "kernels.h"
 
 namespace alice {
@@ -23,6 +33,12 @@ namespace alice {
 constexpr uint32_t kRansL = 1u << 23;   // rans.rs:244
 constexpr uint32_t kProbBits = 12;      // rans.rs:50
 constexpr uint32_t kProbScale = 1u << 12;
+
+// EncSym.packed flag bits
+constexpr uint32_t kEncSmall = 1u << 24;   // freq <= 16: may need two renormalisation bytes
+constexpr uint32_t kEncWide = 1u << 25;    // freq > 4096 (u16-wrapped last symbol)
+constexpr uint32_t kEncZero = 1u << 26;    // freq == 0: the reference divides by zero
+constexpr uint32_t kEncOne = 1u << 27;     // freq == 1: the reciprocal does not fit 32 bits
 
 // ------------------------------------------------------------------------ table building
 ALICE_D uint32_t pack_dec(uint32_t sym, uint32_t freq, uint32_t bias) {
@@ -74,10 +90,13 @@ k_build_tables(const unsigned *__restrict__ hist, int n_symbols, EncSym *__restr
         }
         for (int i = n; i < 256; i++) { s_freq[i] = 0; s_cum[i] = 0; }
         const uint32_t fl = s_freq[n - 1];
+        const bool last_wide = !(fl >= 1 && fl <= kProbScale);
         DecAux a;
-        a.wide_sym = (fl >= 1 && fl <= kProbScale) ? 0xffffffffu : (uint32_t)(n - 1);
+        a.wide_sym = last_wide ? (uint32_t)(n - 1) : 0xffffffffu;
         a.wide_freq = fl;
-        a.pad[0] = a.pad[1] = 0;
+        // the decoder can meet the out-of-range last symbol only if its slot range starts below 4096
+        a.wide_reachable = (last_wide && fl != 0 && s_cum[n - 1] < kProbScale) ? 1u : 0u;
+        a.reserved = 0;
         aux[stream] = a;
     }
     __syncthreads();
@@ -85,18 +104,23 @@ k_build_tables(const unsigned *__restrict__ hist, int n_symbols, EncSym *__restr
     {   // encoder entry of symbol `tid`
         const uint32_t f = s_freq[tid], cum = s_cum[tid];
         EncSym e;
-        const bool zero = (f == 0), slow = (f > kProbScale);
+        const bool zero = (f == 0), wide = (f > kProbScale), one = (f == 1), small = (f >= 2 && f <= 16);
         e.x_lim = zero ? 0u : (f >= 8192u ? 0xffffffffu : (f << 19) - 1u);
         uint32_t sh = 0, rcp = 0;
-        if (!zero && !slow) {
-            const uint32_t L = (f <= 1) ? 0u : (32u - (uint32_t)__clz((int)(f - 1)));  // ceil(log2 f)
-            sh = L > 0 ? L - 1 : 0;
-            const unsigned long long p = 1ull << (32 + sh);
-            rcp = (uint32_t)((p + f - 1) / f - 1);
+        if (f >= 2 && !wide) {
+            // floor(x / f) == (umulhi(x, rcp)) >> sh for every x < 2^31 + 2^15 (DESIGN.md "exact division")
+            if ((f & (f - 1)) == 0) {
+                sh = 30u - (uint32_t)__clz((int)f);            // log2(f) - 1
+                rcp = 0x80000000u;
+            } else {
+                sh = 31u - (uint32_t)__clz((int)f);            // floor(log2 f)
+                rcp = (uint32_t)((1ull << (32 + sh)) / f) + 1u;
+            }
         }
         e.rcp = rcp;
         e.cmpl = kProbScale - f;
-        e.packed = cum | (sh << 16) | ((slow ? 1u : 0u) << 24) | ((zero ? 1u : 0u) << 25);
+        e.packed = cum | (sh << 16) | (small ? kEncSmall : 0u) | (wide ? kEncWide : 0u) | (zero ? kEncZero : 0u) |
+                   (one ? kEncOne : 0u);
         enc[(size_t)stream * 256 + tid] = e;
         if (freq_out) freq_out[(size_t)stream * 256 + tid] = (uint16_t)f;
         if (cum_out) cum_out[(size_t)stream * 256 + tid] = (uint16_t)cum;
@@ -129,105 +153,159 @@ void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *
 }
 
 // --------------------------------------------------------------------------------- encode
-struct EncState {
-    uint32_t x;
-    uint8_t *wp;        // next byte goes to *--wp
-    uint8_t *floor;     // lowest address that may be written
-    uint32_t status;    // 0 ok, 1 overflow, 2 zero-frequency symbol
-};
-
-ALICE_D void enc_put(EncState &s, uint32_t byte, int lane) {
-    if (s.wp > s.floor) {
-        --s.wp;
-        if (lane == 0) *s.wp = (uint8_t)byte;
-    } else {
-        s.status |= 1u;
-    }
-}
-
-// rans.rs:269-285 RansEncoder::encode for one expanded table entry
-ALICE_D void enc_symbol(EncState &s, const EncSym &e, int lane) {
-    uint32_t x = s.x;
-    if (x > e.x_lim) {                      // while (x >= x_max): at most two rounds for freq >= 1
-        enc_put(s, x & 0xff, lane);
-        x >>= 8;
-        if (x > e.x_lim) {
-            enc_put(s, x & 0xff, lane);
-            x >>= 8;
-        }
-    }
-    uint32_t q;
-    if (e.packed >> 24) {                   // rare: freq > 4096 (malformed last symbol) or freq == 0
-        if (e.packed & (1u << 25)) { s.status |= 2u; q = 0; }
-        else q = x / (kProbScale - e.cmpl);
-    } else {
-        // x / freq for x < freq * 2^19: exact with rcp = ceil(2^(32+sh)/freq) - 1
-        unsigned long long p = (unsigned long long)x * e.rcp + e.rcp;
-        q = (uint32_t)(p >> 32) >> ((e.packed >> 16) & 0xff);
-    }
-    // (q << 12) + (x - q*freq) + cum  ==  x + cum + q * (4096 - freq)   (mod 2^32)
-    s.x = x + (e.packed & 0xffffu) + q * e.cmpl;
-}
+constexpr int kEncBlock = 512;                  // symbols per warp-wide fetch (16 bytes per lane)
+constexpr int kEncRing = 2 * kEncBlock + 64;    // bytes one block can emit (2 per symbol) + the 4 state bytes + slack
+constexpr uint32_t kGrpSmall = 1u, kGrpGeneric = 2u;
 
 __global__ void ALICE_LAUNCH_BOUNDS(32, 1)
 k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ enc_all,
               unsigned long long *__restrict__ results) {
-    __shared__ EncSym tab[256];
+    __shared__ uint4 tab[256];                       // EncSym of every symbol
+    __shared__ uint4 st_a[kEncBlock];                // staged per symbol of the block: {x_lim, rcp, cmpl, cum}
+    __shared__ uint2 st_b[kEncBlock];                // {sh, x_lim2}
+    __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
+    __shared__ uint8_t st_sym[kEncBlock];            // the symbols themselves (generic path)
+    __shared__ __align__(16) uint8_t ring[kEncRing]; // emitted bytes of the block, filled from the top down
     const int stream = blockIdx.x;
     const int lane = threadIdx.x;
+    const bool lane0 = lane == 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(enc_all + (size_t)stream * 256);
-        uint4 *dst = reinterpret_cast<uint4 *>(tab);
-        for (int i = lane; i < 256; i += 32) dst[i] = src[i];
+        for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     __syncwarp();
     const RansEncJob job = jobs[stream];
     const uint8_t *sym = job.symbols;
-    EncState s;
-    s.x = kRansL;
-    s.wp = job.out + job.cap;
-    s.floor = job.out;
-    s.status = 0;
+    uint8_t *wp = job.out + job.cap;        // the stream ends at out + cap and grows downwards
+    uint32_t x = kRansL;                    // rans.rs:244
+    uint32_t sp = kEncRing;                 // next byte goes to ring[--sp]
+    uint32_t status = 0;                    // 1 overflow, 2 zero-frequency symbol
+    auto room = [&](uint32_t need) { return (unsigned long long)(wp - job.out) >= need; };
+
+    // generic step, any frequency (rans.rs:269-285 literally)
+    auto step_generic = [&](const uint4 e) {
+        if (e.w & kEncZero) { status |= 2u; return; }
+        while (x > e.x) {                   // while x >= freq << 19 (limit saturated for freq >= 8192: never)
+            --sp;
+            ring[sp] = (uint8_t)x;          // every lane stores the same byte (see the note at the state loop)
+            x >>= 8;
+        }
+        const uint32_t f = kProbScale - e.z;
+        const uint32_t q = x / f;
+        x = x + (e.w & 0xffffu) + q * e.z;  // (q << 12) + x % f + cum
+    };
+    // move ring[sp, kEncRing) to the stream (which grows towards lower addresses) and reset the ring
+    auto flush = [&]() {
+        __syncwarp();
+        const uint32_t n = (uint32_t)kEncRing - sp;
+        uint8_t *dst = wp - n;
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = ring[sp + i];
+        wp = dst;
+        sp = kEncRing;
+        __syncwarp();
+    };
 
     long long i = (long long)job.n;  // symbols [0, i) remain; encode from the back (rans.rs:288-294)
     // ragged tail until the read pointer is 16-byte aligned
-    while (i > 0 && ((reinterpret_cast<uintptr_t>(sym + i)) & 15) != 0) {
-        enc_symbol(s, tab[__ldg(sym + i - 1)], lane);
+    if (!room(64)) status |= 1u;
+    while (i > 0 && ((reinterpret_cast<uintptr_t>(sym + i)) & 15) != 0 && status == 0) {
+        step_generic(tab[__ldg(sym + i - 1)]);
         i--;
     }
-    // full 512-symbol blocks: one coalesced 16-byte load per lane, broadcast chunk by chunk
+    flush();
+    // full 512-symbol blocks: one coalesced 16-byte load per lane
     uint4 cur = make_uint4(0, 0, 0, 0);
-    if (i >= 512) cur = __ldg(reinterpret_cast<const uint4 *>(sym + i - 512) + lane);
-    while (i >= 512 && s.status == 0) {
+    if (i >= kEncBlock) cur = __ldg(reinterpret_cast<const uint4 *>(sym + i - kEncBlock) + lane);
+    while (i >= kEncBlock && status == 0) {
+        if (!room(2 * kEncBlock)) { status |= 1u; break; }
         uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (i >= 1024) nxt = __ldg(reinterpret_cast<const uint4 *>(sym + i - 1024) + lane);
-        for (int c = 31; c >= 0; c--) {
-            uint32_t wd[4];
-            wd[0] = __shfl_sync(kFullMask, cur.x, c);
-            wd[1] = __shfl_sync(kFullMask, cur.y, c);
-            wd[2] = __shfl_sync(kFullMask, cur.z, c);
-            wd[3] = __shfl_sync(kFullMask, cur.w, c);
-            EncSym e[16];  // expand all 16 entries first: keeps shared loads off the state chain
+        if (i >= 2 * kEncBlock) nxt = __ldg(reinterpret_cast<const uint4 *>(sym + i - 2 * kEncBlock) + lane);
+        // ---- all lanes: expand this lane's 16 symbols into ready-to-use table entries
+        {
+            const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
+            uint32_t fl = 0;
 #pragma unroll
-            for (int b = 0; b < 16; b++) e[b] = tab[(wd[b >> 2] >> (8 * (b & 3))) & 0xff];
-#pragma unroll
-            for (int b = 15; b >= 0; b--) enc_symbol(s, e[b], lane);
+            for (int b = 0; b < 16; b++) {
+                const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
+                const uint4 t = tab[sy];
+                st_sym[lane * 16 + b] = (uint8_t)sy;
+                const uint32_t flags = t.w >> 24;
+                st_a[lane * 16 + b] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
+                st_b[lane * 16 + b] = make_uint2((t.w >> 16) & 0xffu,
+                                                 (t.w & kEncSmall) ? ((t.x << 8) | 0xffu) : 0xffffffffu);
+                fl |= flags;
+            }
+            grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
+                        ((fl & ((kEncWide | kEncZero | kEncOne) >> 24)) ? kGrpGeneric : 0u);
         }
+        __syncwarp();
+        // ---- the state recurrence, last symbol first.  Every lane computes the same values and performs the same
+        // ring stores (same address, same data), so the result does not depend on how the lanes interleave.
+        for (int c = 31; c >= 0; c--) {
+            const uint32_t g = grp[c];
+            if (!(g & kGrpGeneric)) {
+                // entries of the whole group first: the loads are independent of the state
+                uint4 ea[16];
+                uint2 eb[16];
+#pragma unroll
+                for (int b = 0; b < 16; b++) { ea[b] = st_a[c * 16 + b]; eb[b] = st_b[c * 16 + b]; }
+                smem_addr_t spa = smem_addr_of(ring) + sp;     // the next byte goes to spa[-1]
+                const smem_addr_t spa0 = spa;
+                if (g == 0) {
+                    // every freq in (16, 4096]: at most one renormalisation byte per symbol
+#pragma unroll
+                    for (int b = 15; b >= 0; b--) {
+                        const bool k = x > ea[b].x;
+                        uint32_t q = __umulhi(x, ea[b].y) >> eb[b].x;   // floor(x / freq), independent of k
+                        q = k ? (q >> 8) : q;              // floor(floor(x/f) / 256) == floor(floor(x/256) / f)
+                        smem_st_u8<-1>(spa, x);            // unconditional: overwritten later unless k
+                        spa -= k ? 1 : 0;
+                        const uint32_t xs = k ? (x >> 8) : x;
+                        x = q * ea[b].z + (xs + ea[b].w);
+                    }
+                } else {
+                    // some freq in [2, 16]: up to two renormalisation bytes
+#pragma unroll
+                    for (int b = 15; b >= 0; b--) {
+                        const bool k1 = x > ea[b].x, k2 = x > eb[b].y;
+                        uint32_t q = __umulhi(x, ea[b].y) >> eb[b].x;
+                        q = k1 ? (q >> 8) : q;
+                        q = k2 ? (q >> 8) : q;
+                        smem_st_u8<-1>(spa, x);
+                        smem_st_u8<-2>(spa, x >> 8);
+                        spa -= (k1 ? 1 : 0) + (k2 ? 1 : 0);
+                        uint32_t xs = k1 ? (x >> 8) : x;
+                        xs = k2 ? (x >> 16) : xs;
+                        x = q * ea[b].z + (xs + ea[b].w);
+                    }
+                }
+                sp -= (uint32_t)(spa0 - spa);
+            } else {
+                for (int b = 15; b >= 0 && status == 0; b--) step_generic(tab[st_sym[c * 16 + b]]);
+                if (status) break;
+            }
+        }
+        flush();
         cur = nxt;
-        i -= 512;
+        i -= kEncBlock;
     }
-    while (i > 0 && s.status == 0) {
-        enc_symbol(s, tab[__ldg(sym + i - 1)], lane);
+    if (status == 0 && !room(2 * kEncBlock + 8)) status |= 1u;
+    while (i > 0 && status == 0) {
+        step_generic(tab[__ldg(sym + i - 1)]);
         i--;
     }
     // finish (rans.rs:298-308): 4 state bytes, low byte first, then the whole vector is reversed
-    enc_put(s, s.x & 0xff, lane);
-    enc_put(s, (s.x >> 8) & 0xff, lane);
-    enc_put(s, (s.x >> 16) & 0xff, lane);
-    enc_put(s, (s.x >> 24) & 0xff, lane);
-    if (lane == 0) {
-        results[2 * stream] = (unsigned long long)((job.out + job.cap) - s.wp);
-        results[2 * stream + 1] = s.status;
+    if (status == 0) {
+        ring[sp - 1] = (uint8_t)x;
+        ring[sp - 2] = (uint8_t)(x >> 8);
+        ring[sp - 3] = (uint8_t)(x >> 16);
+        ring[sp - 4] = (uint8_t)(x >> 24);
+        sp -= 4;
+        flush();
+    }
+    if (lane0) {
+        results[2 * stream] = (unsigned long long)((job.out + job.cap) - wp);
+        results[2 * stream + 1] = status;
     }
 }
 
@@ -238,32 +316,31 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
 }
 
 // --------------------------------------------------------------------------------- decode
+constexpr int kDecBlock = 512;                   // symbols per fast block (one 16-byte store per lane)
+constexpr int kWinPos = 2048;                    // byte positions held by the window ring
+constexpr int kWinMirror = 2 * kDecBlock + 16;   // positions mirrored past the end: a block reads linearly
+constexpr int kWinFill = 512;                    // bytes converted per refill (16 per lane)
+// window entry of position p: {bytes p..p+3, bytes p+4..p+7} as two big-endian words; 8 bytes per position makes
+// the renormalisation shift (8 bits per byte) equal to the address increment
+constexpr int kDecSmemBytes = kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
+
 struct DecState {
     uint32_t x;
     unsigned long long pos, len;
     const uint8_t *in;
-    uint32_t nb;  // in[pos], pre-loaded (0 past the end)
 };
 
-// rans.rs:351-371 RansDecoder::decode
-ALICE_D uint32_t dec_symbol(DecState &s, const uint32_t *lut, uint32_t f0c, uint32_t f0, uint32_t wide_sym,
-                            uint32_t wide_freq) {
+// generic step (rans.rs:351-371 literally), reading stream bytes from global memory
+ALICE_D uint32_t dec_step_generic(DecState &s, const uint2 *ent, const uint8_t *symt, uint32_t wide_sym,
+                                  uint32_t wide_freq) {
     const uint32_t slot = s.x & (kProbScale - 1);
-    uint32_t sym;
-    if (slot < f0c) {          // symbol 0 owns slots [0, freq0): no table access on the hot path
-        sym = 0;
-        s.x = f0 * (s.x >> kProbBits) + slot;
-    } else {
-        const uint32_t ent = lut[slot];
-        sym = ent & 0xff;
-        uint32_t f = ((ent >> 8) & 0xfff) + 1;
-        if (sym == wide_sym) f = wide_freq;
-        s.x = f * (s.x >> kProbBits) + (ent >> 20);   // low 32 bits of the reference's u64 expression
-    }
+    const uint2 e = ent[slot];
+    const uint32_t sym = symt[slot];
+    const uint32_t f = (sym == wide_sym) ? wide_freq : e.x;
+    s.x = f * (s.x >> kProbBits) + e.y;          // low 32 bits of the reference's u64 expression
     while (s.x < kRansL && s.pos < s.len) {
-        s.x = (s.x << 8) | s.nb;
+        s.x = (s.x << 8) | (uint32_t)__ldg(s.in + s.pos);
         s.pos++;
-        s.nb = s.pos < s.len ? (uint32_t)__ldg(s.in + s.pos) : 0u;
     }
     return sym;
 }
@@ -271,13 +348,21 @@ ALICE_D uint32_t dec_symbol(DecState &s, const uint32_t *lut, uint32_t f0c, uint
 __global__ void ALICE_LAUNCH_BOUNDS(32, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
               const DecAux *__restrict__ aux_all) {
-    __shared__ uint32_t lut[kDecLutEntries];
+    ALICE_DYN_SMEM(smem);
+    uint2 *ent = reinterpret_cast<uint2 *>(smem);                               // slot -> {freq, slot - cum}
+    uint2 *win = reinterpret_cast<uint2 *>(smem + kDecLutEntries * 8);          // position -> next 8 bytes, big-endian
+    uint8_t *symt = smem + kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8;     // slot -> symbol
+    uint16_t *slots = reinterpret_cast<uint16_t *>(symt + kDecLutEntries);      // slots decoded in this block
     const int stream = blockIdx.x;
     const int lane = threadIdx.x;
+    const bool lane0 = lane == 0;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(lut_all + (size_t)stream * kDecLutEntries);
-        uint4 *dst = reinterpret_cast<uint4 *>(lut);
-        for (int i = lane; i < kDecLutEntries / 4; i += 32) dst[i] = src[i];
+        const uint32_t *src = lut_all + (size_t)stream * kDecLutEntries;
+        for (int i = lane; i < kDecLutEntries; i += 32) {
+            const uint32_t p = src[i];
+            ent[i] = make_uint2(((p >> 8) & 0xfffu) + 1u, p >> 20);
+            symt[i] = (uint8_t)p;
+        }
     }
     __syncwarp();
     const RansDecJob job = jobs[stream];
@@ -292,35 +377,147 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
               (uint32_t)__ldg(s.in + 3);
         s.pos = 4;
     }
-    s.nb = s.pos < s.len ? (uint32_t)__ldg(s.in + s.pos) : 0u;
-    const uint32_t ent0 = lut[0];
-    uint32_t f0 = ((ent0 >> 8) & 0xfff) + 1, f0c = 0;
-    if ((ent0 & 0xff) == 0 && (ent0 >> 20) == 0 && aux.wide_sym != 0) f0c = f0;  // slots [0,f0) decode to symbol 0
+    // symbol 0 owns slots [0, freq0) when it is an ordinary symbol: no table access on the hot path
+    const uint32_t f0 = ent[0].x;
+    uint32_t f0c = 0;
+    if (symt[0] == 0 && ent[0].y == 0 && aux.wide_sym != 0) f0c = f0 < kProbScale ? f0 : kProbScale;
+    const bool fast_ok = aux.wide_reachable == 0;
+
+    // window ring over byte offsets relative to the 16-byte aligned address below job.in
+    const uintptr_t in_addr = reinterpret_cast<uintptr_t>(job.in);
+    const uint8_t *ga = reinterpret_cast<const uint8_t *>(in_addr & ~(uintptr_t)15);
+    const unsigned long long skew = in_addr & 15;             // offset of stream byte 0 from ga
+    const unsigned long long end_off = skew + s.len;          // offsets >= end_off are not stream bytes
+    unsigned long long filled = 0;                            // window valid for offsets [.., filled)
+    bool win_started = false;
 
     uint8_t *out = job.symbols;
     unsigned long long i = 0;
     const unsigned long long n = job.n;
-    while (i < n && ((reinterpret_cast<uintptr_t>(out + i)) & 3) != 0) {
-        uint32_t sy = dec_symbol(s, lut, f0c, f0, aux.wide_sym, aux.wide_freq);
-        if (lane == 0) out[i] = (uint8_t)sy;
-        i++;
+
+    auto careful = [&](unsigned long long upto) {   // generic steps for symbols [i, upto); true if the rest was filled
+        for (; i < upto; i++) {
+            const uint32_t xb = s.x;
+            const uint32_t sy = dec_step_generic(s, ent, symt, aux.wide_sym, aux.wide_freq);
+            if (lane0) out[i] = (uint8_t)sy;
+            if (s.pos >= s.len && s.x == xb) {
+                // exhausted stream and a fixed point of the state map: every further symbol is `sy`
+                for (unsigned long long j = i + 1 + lane; j < n; j += 32) out[j] = (uint8_t)sy;
+                i = n;
+                return true;
+            }
+        }
+        return false;
+    };
+
+    // peel until the output pointer is 16-byte aligned
+    {
+        unsigned long long peel = (16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15;
+        if (peel > n) peel = n;
+        careful(peel);
     }
-    for (; i + 4 <= n; i += 4) {
-        uint32_t pk = 0;
+    while (i < n) {
+        const bool fast = fast_ok && (n - i) >= (unsigned long long)kDecBlock && s.x >= kRansL &&
+                          s.pos + 2ull * kDecBlock <= s.len;
+        if (!fast) {
+            unsigned long long upto = i + kDecBlock;
+            if (upto > n) upto = n;
+            if (careful(upto)) break;
+            continue;
+        }
+        // ---- make the window cover offsets [o, o + 2*kDecBlock + 12)
+        const unsigned long long o = skew + s.pos;
+        if (!win_started || o >= filled) { filled = o & ~(unsigned long long)15; win_started = true; }
+        while (filled < o + 2ull * kDecBlock + 12) {
+            __syncwarp();
+            {
+                const unsigned long long base = filled + 16ull * lane;
+                uint32_t d[6];
+                if (base < end_off) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ga + base));
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                } else { d[0] = d[1] = d[2] = d[3] = 0; }
+                if (base + 16 < end_off) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base + 16));
+                    d[4] = v.x; d[5] = v.y;
+                } else { d[4] = d[5] = 0; }
+                uint32_t be[20];   // be[k] = big-endian word of bytes base+k .. base+k+3
 #pragma unroll
-        for (int b = 0; b < 4; b++) pk |= dec_symbol(s, lut, f0c, f0, aux.wide_sym, aux.wide_freq) << (8 * b);
-        if (lane == 0) *reinterpret_cast<uint32_t *>(out + i) = pk;
-    }
-    for (; i < n; i++) {
-        uint32_t sy = dec_symbol(s, lut, f0c, f0, aux.wide_sym, aux.wide_freq);
-        if (lane == 0) out[i] = (uint8_t)sy;
+                for (int k = 0; k < 20; k++)
+                    be[k] = __byte_perm(__funnelshift_r(d[k >> 2], d[(k >> 2) + 1 > 5 ? 5 : (k >> 2) + 1], 8 * (k & 3)), 0, 0x0123);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t idx = (uint32_t)((base + k) & (kWinPos - 1));
+                    const uint2 e = make_uint2(be[k], be[k + 4]);
+                    win[idx] = e;
+                    if (idx < (uint32_t)kWinMirror) win[kWinPos + idx] = e;
+                }
+            }
+            filled += kWinFill;
+            __syncwarp();
+        }
+        // ---- 512 symbols, state recurrence only; every lane computes the same values
+        uint32_t x = s.x;
+        const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
+        const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
+        smem_addr_t wa = wa0;                                 // running window address: 8 bytes per stream byte
+        uint32_t v = win[wi0].x;                              // the next four stream bytes, big-endian
+        for (int g = 0; g < kDecBlock / 16; g++) {
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t slot = x & (kProbScale - 1);
+                const uint32_t xs = x >> kProbBits;
+                const uint32_t lo = smem_ld_u32<4>(wa);       // the four bytes after v; address known one symbol early
+                slots[g * 16 + b] = (uint16_t)slot;           // all lanes, same value
+                uint32_t f = f0, bias = slot;
+                if (slot >= f0c) {
+                    const uint2 e = ent[slot];
+                    f = e.x;
+                    bias = e.y;
+                }
+                x = f * xs + bias;
+                // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
+                const bool ka = x < kRansL, kb = x < (1u << 15);
+                uint32_t sa = ka ? 8u : 0u;
+                sa = kb ? 16u : sa;
+                x = __funnelshift_l(v, x, sa);
+                v = __funnelshift_l(lo, v, sa);
+                wa += sa;                                     // 8 address bytes per consumed stream byte
+            }
+        }
+        s.x = x;
+        s.pos += (unsigned long long)(wa - wa0) / 8;
+        __syncwarp();
+        // ---- all lanes: slot -> symbol for 16 symbols each, one 16-byte store per lane
+        {
+            const uint4 sv0 = *reinterpret_cast<const uint4 *>(slots + 16 * lane);
+            const uint4 sv1 = *reinterpret_cast<const uint4 *>(slots + 16 * lane + 8);
+            const uint32_t sw[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t a = symt[sw[2 * k] & 0xffffu], b2 = symt[sw[2 * k] >> 16];
+                const uint32_t c2 = symt[sw[2 * k + 1] & 0xffffu], d2 = symt[sw[2 * k + 1] >> 16];
+                ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
+            }
+            *reinterpret_cast<uint4 *>(out + i + 16 * lane) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        __syncwarp();
+        i += kDecBlock;
     }
 }
 
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
                  cudaStream_t st) {
     if (n_streams <= 0) return;
-    ALICE_LAUNCH(k_rans_decode, dim3(n_streams), dim3(32), 0, st, d_jobs, d_dec_lut, d_aux);
+#ifndef ALICE_EMUL
+    static bool attr_set = false;   // idempotent; a race only repeats the call
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_rans_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes);
+        attr_set = true;
+    }
+#endif
+    ALICE_LAUNCH(k_rans_decode, dim3(n_streams), dim3(32), kDecSmemBytes, st, d_jobs, d_dec_lut, d_aux);
 }
 
 }  // namespace alice

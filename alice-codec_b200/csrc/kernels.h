@@ -17,17 +17,22 @@ void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uin
                      int pw, int ph, int pf, const int steps[3], cudaStream_t st);
 
 // ---- rANS (k_rans.cu) ------------------------------------------------------------------
-struct EncSym {          // one per symbol, 16 bytes
+struct EncSym {          // one per symbol, 16 bytes (read as one uint4 {x_lim, rcp, cmpl, packed})
     uint32_t x_lim;      // renormalise while x > x_lim   (= freq * 2^19 - 1, saturated)
-    uint32_t rcp;        // ceil(2^(32+sh)/freq) - 1
+    uint32_t rcp;        // floor(x / freq) == ((x * rcp + rcp) >> 32) >> sh   for x < 2^31 + 2^15
     uint32_t cmpl;       // 4096 - freq  (mod 2^32)
-    uint32_t packed;     // cum (16) | sh << 16 (8) | slow << 24 | zero_freq << 25
+    uint32_t packed;     // cum (16) | sh << 16 (8) | small(freq <= 16) << 24 | wide(freq > 4096) << 25 | zero << 26
 };
 struct DecAux {          // per stream
     uint32_t wide_sym;   // symbol whose freq is outside [1, 4096] (only the last symbol can be), or 0xffffffff
     uint32_t wide_freq;
-    uint32_t pad[2];
+    uint32_t wide_reachable;  // 1 if the decoder LUT maps at least one slot to wide_sym
+    uint32_t reserved;
 };
+// the encoder checks for output room once per 512-symbol block, so a stream buffer must hold the worst case
+// (2 bytes per symbol + 4 state bytes, rans.rs:269-308) plus one block of slack
+constexpr size_t kRansEncSlack = 1104;
+inline size_t rans_enc_worst_case(size_t n_symbols) { return (2 * n_symbols + 4 + kRansEncSlack + 15) / 16 * 16; }
 constexpr int kEncTableBytes = 256 * (int)sizeof(EncSym);
 constexpr int kDecLutEntries = 4096;
 

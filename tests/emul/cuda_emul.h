@@ -235,6 +235,9 @@ inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) {
     return (unsigned)(((((uint64_t)hi) << 32) | lo) >> (s & 31));
 }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
+    return (unsigned)((((((uint64_t)hi) << 32) | lo) << (s & 31)) >> 32);
+}
 inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     uint64_t v = ((uint64_t)b << 32) | a;
     unsigned r = 0;

@@ -162,7 +162,8 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
               unsigned long long *__restrict__ results) {
     __shared__ uint4 tab[256];                       // EncSym of every symbol
     __shared__ uint4 st_a[kEncBlock];                // staged per symbol of the block: {x_lim, rcp, cmpl, cum}
-    __shared__ uint2 st_b[kEncBlock];                // {sh, x_lim2}
+    __shared__ uint4 st_b[kEncBlock];                // {sh, sh + 8, sh + 16, x_lim2 (two-byte limit, freq <= 16)}
+    __shared__ uint32_t st_x[kEncBlock];             // state before the step of each symbol
     __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
     __shared__ uint8_t st_sym[kEncBlock];            // the symbols themselves (generic path)
     __shared__ __align__(16) uint8_t ring[kEncRing]; // emitted bytes of the block, filled from the top down
@@ -228,62 +229,98 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             for (int b = 0; b < 16; b++) {
                 const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
                 const uint4 t = tab[sy];
+                const uint32_t sh = (t.w >> 16) & 0xffu;
                 st_sym[lane * 16 + b] = (uint8_t)sy;
-                const uint32_t flags = t.w >> 24;
                 st_a[lane * 16 + b] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_b[lane * 16 + b] = make_uint2((t.w >> 16) & 0xffu,
+                st_b[lane * 16 + b] = make_uint4(sh, sh + 8u, sh + 16u,
                                                  (t.w & kEncSmall) ? ((t.x << 8) | 0xffu) : 0xffffffffu);
-                fl |= flags;
+                fl |= t.w >> 24;
             }
             grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
                         ((fl & ((kEncWide | kEncZero | kEncOne) >> 24)) ? kGrpGeneric : 0u);
         }
         __syncwarp();
-        // ---- the state recurrence, last symbol first.  Every lane computes the same values and performs the same
-        // ring stores (same address, same data), so the result does not depend on how the lanes interleave.
-        for (int c = 31; c >= 0; c--) {
-            const uint32_t g = grp[c];
-            if (!(g & kGrpGeneric)) {
-                // entries of the whole group first: the loads are independent of the state
-                uint4 ea[16];
-                uint2 eb[16];
+        // ---- lane 0 only: the state recurrence, last symbol first.  It records the state before each step in
+        // st_x; which bytes that step emitted is recomputed from (state, limit) by all lanes afterwards, so the
+        // serial code has no stream pointer to maintain.  (One active lane also makes every 16-byte shared load a
+        // single wavefront.)
+        if (lane0) {
+            for (int c = 31; c >= 0; c--) {
+                const uint32_t g = grp[c];
+                if (!(g & kGrpGeneric)) {
+                    uint4 ea[16];
+                    uint4 eb[16];
 #pragma unroll
-                for (int b = 0; b < 16; b++) { ea[b] = st_a[c * 16 + b]; eb[b] = st_b[c * 16 + b]; }
-                smem_addr_t spa = smem_addr_of(ring) + sp;     // the next byte goes to spa[-1]
-                const smem_addr_t spa0 = spa;
-                if (g == 0) {
-                    // every freq in (16, 4096]: at most one renormalisation byte per symbol
+                    for (int b = 0; b < 16; b++) { ea[b] = st_a[c * 16 + b]; eb[b] = st_b[c * 16 + b]; }
+                    if (g == 0) {
+                        // every freq in (16, 4096]: at most one renormalisation byte per symbol
 #pragma unroll
-                    for (int b = 15; b >= 0; b--) {
-                        const bool k = x > ea[b].x;
-                        uint32_t q = __umulhi(x, ea[b].y) >> eb[b].x;   // floor(x / freq), independent of k
-                        q = k ? (q >> 8) : q;              // floor(floor(x/f) / 256) == floor(floor(x/256) / f)
-                        smem_st_u8<-1>(spa, x);            // unconditional: overwritten later unless k
-                        spa -= k ? 1 : 0;
-                        const uint32_t xs = k ? (x >> 8) : x;
-                        x = q * ea[b].z + (xs + ea[b].w);
+                        for (int b = 15; b >= 0; b--) {
+                            st_x[c * 16 + b] = x;
+                            const bool k = x > ea[b].x;
+                            const uint32_t hi = __umulhi(x, ea[b].y);
+                            const uint32_t q = hi >> (k ? eb[b].y : eb[b].x);   // floor(floor(x/f)/256^k) == floor((x>>8k)/f)
+                            const uint32_t xs = x >> (k ? 8u : 0u);
+                            x = q * ea[b].z + (xs + ea[b].w);
+                        }
+                    } else {
+                        // some freq in [2, 16]: up to two renormalisation bytes
+#pragma unroll
+                        for (int b = 15; b >= 0; b--) {
+                            st_x[c * 16 + b] = x;
+                            const bool k1 = x > ea[b].x, k2 = x > eb[b].w;
+                            const uint32_t hi = __umulhi(x, ea[b].y);
+                            uint32_t sq = k1 ? eb[b].y : eb[b].x;
+                            sq = k2 ? eb[b].z : sq;
+                            uint32_t sx = k1 ? 8u : 0u;
+                            sx = k2 ? 16u : sx;
+                            x = (hi >> sq) * ea[b].z + ((x >> sx) + ea[b].w);
+                        }
                     }
                 } else {
-                    // some freq in [2, 16]: up to two renormalisation bytes
-#pragma unroll
                     for (int b = 15; b >= 0; b--) {
-                        const bool k1 = x > ea[b].x, k2 = x > eb[b].y;
-                        uint32_t q = __umulhi(x, ea[b].y) >> eb[b].x;
-                        q = k1 ? (q >> 8) : q;
-                        q = k2 ? (q >> 8) : q;
-                        smem_st_u8<-1>(spa, x);
-                        smem_st_u8<-2>(spa, x >> 8);
-                        spa -= (k1 ? 1 : 0) + (k2 ? 1 : 0);
-                        uint32_t xs = k1 ? (x >> 8) : x;
-                        xs = k2 ? (x >> 16) : xs;
-                        x = q * ea[b].z + (xs + ea[b].w);
+                        const uint4 e = tab[st_sym[c * 16 + b]];
+                        st_x[c * 16 + b] = x;
+                        if (e.w & kEncZero) { status |= 2u; continue; }
+                        while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
+                        const uint32_t f = kProbScale - e.z;
+                        const uint32_t q = x / f;
+                        x = x + (e.w & 0xffffu) + q * e.z;
                     }
                 }
-                sp -= (uint32_t)(spa0 - spa);
-            } else {
-                for (int b = 15; b >= 0 && status == 0; b--) step_generic(tab[st_sym[c * 16 + b]]);
-                if (status) break;
             }
+        }
+        __syncwarp();
+        x = __shfl_sync(kFullMask, x, 0);
+        status = __shfl_sync(kFullMask, status, 0);
+        if (status) break;
+        // ---- all lanes: lane c emits the bytes of group c.  A step that started in state s with limit L emitted
+        // s & 0xff if s > L and then (s >> 8) & 0xff if (s >> 8) > L (at most two bytes, rans.rs:275-279).
+        {
+            uint32_t kb1 = 0, kb2 = 0;   // bit b: symbol b of my group emitted a first / second byte
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t sx = st_x[lane * 16 + b], lim = st_a[lane * 16 + b].x;
+                kb1 |= (sx > lim ? 1u : 0u) << b;
+                kb2 |= ((sx > lim) && ((sx >> 8) > lim) ? 1u : 0u) << b;
+            }
+            const uint32_t mine = (uint32_t)(__popc(kb1) + __popc(kb2));
+            // bytes emitted before mine = those of the groups processed earlier = lanes above me
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_down_sync(kFullMask, incl, d);
+                if (lane + d < 32) incl += o;
+            }
+            const uint32_t total = __shfl_sync(kFullMask, incl, 0);
+            uint32_t pos = sp - (incl - mine);          // my first byte goes to ring[pos - 1]
+#pragma unroll
+            for (int b = 15; b >= 0; b--) {
+                const uint32_t sx = st_x[lane * 16 + b];
+                if (kb1 & (1u << b)) ring[--pos] = (uint8_t)sx;
+                if (kb2 & (1u << b)) ring[--pos] = (uint8_t)(sx >> 8);
+            }
+            sp -= total;
         }
         flush();
         cur = nxt;
@@ -377,10 +414,6 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
               (uint32_t)__ldg(s.in + 3);
         s.pos = 4;
     }
-    // symbol 0 owns slots [0, freq0) when it is an ordinary symbol: no table access on the hot path
-    const uint32_t f0 = ent[0].x;
-    uint32_t f0c = 0;
-    if (symt[0] == 0 && ent[0].y == 0 && aux.wide_sym != 0) f0c = f0 < kProbScale ? f0 : kProbScale;
     const bool fast_ok = aux.wide_reachable == 0;
 
     // window ring over byte offsets relative to the 16-byte aligned address below job.in
@@ -461,30 +494,31 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
         const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
         smem_addr_t wa = wa0;                                 // running window address: 8 bytes per stream byte
-        uint32_t v = win[wi0].x;                              // the next four stream bytes, big-endian
-        for (int g = 0; g < kDecBlock / 16; g++) {
+        // ---- lane 0 only (one active lane: every shared access is a single wavefront)
+        if (lane0) {
+            uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
+            for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                const uint32_t slot = x & (kProbScale - 1);
-                const uint32_t xs = x >> kProbBits;
-                const uint32_t lo = smem_ld_u32<4>(wa);       // the four bytes after v; address known one symbol early
-                slots[g * 16 + b] = (uint16_t)slot;           // all lanes, same value
-                uint32_t f = f0, bias = slot;
-                if (slot >= f0c) {
-                    const uint2 e = ent[slot];
-                    f = e.x;
-                    bias = e.y;
+                for (int b = 0; b < 16; b++) {
+                    const uint32_t slot8 = (x << 3) & ((kProbScale - 1) << 3);     // byte offset of ent[slot]
+                    const uint32_t xs = x >> kProbBits;
+                    const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
+                    const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
+                    slots[g * 16 + b] = (uint16_t)slot8;
+                    x = e.x * xs + e.y;
+                    // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
+                    const bool ka = x < kRansL, kb = x < (1u << 15);
+                    uint32_t sa = ka ? 8u : 0u;
+                    sa = kb ? 16u : sa;
+                    x = __funnelshift_l(v, x, sa);
+                    v = __funnelshift_l(lo, v, sa);
+                    wa += sa;                                 // 8 address bytes per consumed stream byte
                 }
-                x = f * xs + bias;
-                // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
-                const bool ka = x < kRansL, kb = x < (1u << 15);
-                uint32_t sa = ka ? 8u : 0u;
-                sa = kb ? 16u : sa;
-                x = __funnelshift_l(v, x, sa);
-                v = __funnelshift_l(lo, v, sa);
-                wa += sa;                                     // 8 address bytes per consumed stream byte
             }
         }
+        __syncwarp();
+        x = __shfl_sync(kFullMask, x, 0);
+        wa = wa0 + __shfl_sync(kFullMask, (uint32_t)(wa - wa0), 0);
         s.x = x;
         s.pos += (unsigned long long)(wa - wa0) / 8;
         __syncwarp();
@@ -496,8 +530,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             uint32_t ow[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t a = symt[sw[2 * k] & 0xffffu], b2 = symt[sw[2 * k] >> 16];
-                const uint32_t c2 = symt[sw[2 * k + 1] & 0xffffu], d2 = symt[sw[2 * k + 1] >> 16];
+                const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> 3], b2 = symt[sw[2 * k] >> 19];
+                const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> 3], d2 = symt[sw[2 * k + 1] >> 19];
                 ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
             }
             *reinterpret_cast<uint4 *>(out + i + 16 * lane) = make_uint4(ow[0], ow[1], ow[2], ow[3]);

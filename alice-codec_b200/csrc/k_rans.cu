@@ -162,7 +162,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
               unsigned long long *__restrict__ results) {
     __shared__ uint4 tab[256];                       // EncSym of every symbol
     __shared__ uint4 st_a[kEncBlock];                // staged per symbol of the block: {x_lim, rcp, cmpl, cum}
-    __shared__ uint4 st_b[kEncBlock];                // {sh, sh + 8, sh + 16, x_lim2 (two-byte limit, freq <= 16)}
+    __shared__ uint32_t st_s[kEncBlock];             // division shift sh | (freq <= 16) << 8
     __shared__ uint32_t st_x[kEncBlock];             // state before the step of each symbol
     __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
     __shared__ uint8_t st_sym[kEncBlock];            // the symbols themselves (generic path)
@@ -229,11 +229,9 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             for (int b = 0; b < 16; b++) {
                 const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
                 const uint4 t = tab[sy];
-                const uint32_t sh = (t.w >> 16) & 0xffu;
                 st_sym[lane * 16 + b] = (uint8_t)sy;
                 st_a[lane * 16 + b] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_b[lane * 16 + b] = make_uint4(sh, sh + 8u, sh + 16u,
-                                                 (t.w & kEncSmall) ? ((t.x << 8) | 0xffu) : 0xffffffffu);
+                st_s[lane * 16 + b] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
                 fl |= t.w >> 24;
             }
             grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
@@ -243,39 +241,48 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
         // ---- lane 0 only: the state recurrence, last symbol first.  It records the state before each step in
         // st_x; which bytes that step emitted is recomputed from (state, limit) by all lanes afterwards, so the
         // serial code has no stream pointer to maintain.  (One active lane also makes every 16-byte shared load a
-        // single wavefront.)
+        // single wavefront.)  Entries of the next group are loaded into each register slot as soon as the
+        // current group has used it, so the loads issue in the shadow of the dependent arithmetic.
         if (lane0) {
+            uint4 ea[16];
+            uint32_t es[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) { ea[b] = st_a[31 * 16 + b]; es[b] = st_s[31 * 16 + b]; }
+            uint32_t g = grp[31];
             for (int c = 31; c >= 0; c--) {
-                const uint32_t g = grp[c];
-                if (!(g & kGrpGeneric)) {
-                    uint4 ea[16];
-                    uint4 eb[16];
+                const int cn = c > 0 ? c - 1 : 0;
+                const uint32_t gn = grp[cn];
+                if (g == 0) {
+                    // every freq in (16, 4096]: at most one renormalisation byte per symbol.  Both outcomes are
+                    // computed and selected at the end, so the comparison is off the critical path.
 #pragma unroll
-                    for (int b = 0; b < 16; b++) { ea[b] = st_a[c * 16 + b]; eb[b] = st_b[c * 16 + b]; }
-                    if (g == 0) {
-                        // every freq in (16, 4096]: at most one renormalisation byte per symbol
+                    for (int b = 15; b >= 0; b--) {
+                        st_x[c * 16 + b] = x;
+                        const bool k = x > ea[b].x;
+                        const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
+                        const uint32_t sh = es[b];
+                        const uint32_t xa = (hi >> sh) * ea[b].z + (x + ea[b].w);
+                        // floor(floor(x/f) / 256) == floor((x >> 8) / f)
+                        const uint32_t xb = (hi >> (sh + 8u)) * ea[b].z + ((x >> 8) + ea[b].w);
+                        x = k ? xb : xa;
+                        ea[b] = st_a[cn * 16 + b];
+                        es[b] = st_s[cn * 16 + b];
+                    }
+                } else if (!(g & kGrpGeneric)) {
+                    // some freq in [2, 16]: up to two renormalisation bytes
 #pragma unroll
-                        for (int b = 15; b >= 0; b--) {
-                            st_x[c * 16 + b] = x;
-                            const bool k = x > ea[b].x;
-                            const uint32_t hi = __umulhi(x, ea[b].y);
-                            const uint32_t q = hi >> (k ? eb[b].y : eb[b].x);   // floor(floor(x/f)/256^k) == floor((x>>8k)/f)
-                            const uint32_t xs = x >> (k ? 8u : 0u);
-                            x = q * ea[b].z + (xs + ea[b].w);
-                        }
-                    } else {
-                        // some freq in [2, 16]: up to two renormalisation bytes
-#pragma unroll
-                        for (int b = 15; b >= 0; b--) {
-                            st_x[c * 16 + b] = x;
-                            const bool k1 = x > ea[b].x, k2 = x > eb[b].w;
-                            const uint32_t hi = __umulhi(x, ea[b].y);
-                            uint32_t sq = k1 ? eb[b].y : eb[b].x;
-                            sq = k2 ? eb[b].z : sq;
-                            uint32_t sx = k1 ? 8u : 0u;
-                            sx = k2 ? 16u : sx;
-                            x = (hi >> sq) * ea[b].z + ((x >> sx) + ea[b].w);
-                        }
+                    for (int b = 15; b >= 0; b--) {
+                        st_x[c * 16 + b] = x;
+                        const uint32_t lim = ea[b].x;
+                        const uint32_t lim2 = (es[b] & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
+                        const uint32_t sh = es[b] & 0xffu;
+                        const bool k1 = x > lim, k2 = x > lim2;
+                        const uint32_t hi = __umulhi(x, ea[b].y);
+                        uint32_t sx = k1 ? 8u : 0u;
+                        sx = k2 ? 16u : sx;
+                        x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
+                        ea[b] = st_a[cn * 16 + b];
+                        es[b] = st_s[cn * 16 + b];
                     }
                 } else {
                     for (int b = 15; b >= 0; b--) {
@@ -287,7 +294,10 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         const uint32_t q = x / f;
                         x = x + (e.w & 0xffffu) + q * e.z;
                     }
+#pragma unroll
+                    for (int b = 0; b < 16; b++) { ea[b] = st_a[cn * 16 + b]; es[b] = st_s[cn * 16 + b]; }
                 }
+                g = gn;
             }
         }
         __syncwarp();
@@ -415,6 +425,23 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         s.pos = 4;
     }
     const bool fast_ok = aux.wide_reachable == 0;
+    // register-resident decode of symbols 0..2 (slot ranges [0,c1), [c1,c2), [c2,c3)); empty ranges if the table
+    // does not start that way
+    uint32_t f0 = 1, f1 = 1, f2 = 1, c1 = 0, c2 = 0, c3 = 0;
+    if (symt[0] == 0 && ent[0].y == 0 && aux.wide_sym != 0) {
+        f0 = ent[0].x;
+        c1 = f0 < kProbScale ? f0 : kProbScale;
+        c2 = c3 = c1;
+        if (c1 < kProbScale && symt[c1] == 1 && ent[c1].y == 0 && aux.wide_sym != 1) {
+            f1 = ent[c1].x;
+            c2 = c1 + f1 < kProbScale ? c1 + f1 : kProbScale;
+            c3 = c2;
+            if (c2 < kProbScale && symt[c2] == 2 && ent[c2].y == 0 && aux.wide_sym != 2) {
+                f2 = ent[c2].x;
+                c3 = c2 + f2 < kProbScale ? c2 + f2 : kProbScale;
+            }
+        }
+    }
 
     // window ring over byte offsets relative to the 16-byte aligned address below job.in
     const uintptr_t in_addr = reinterpret_cast<uintptr_t>(job.in);
@@ -494,25 +521,38 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
         const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
         smem_addr_t wa = wa0;                                 // running window address: 8 bytes per stream byte
-        // ---- lane 0 only (one active lane: every shared access is a single wavefront)
+        // ---- lane 0 only (one active lane: every shared access is a single wavefront).  Symbols 0, 1 and 2 own the
+        // slot ranges [0,c1), [c1,c2), [c2,c3): their {freq, cum} live in registers, so the common symbols do not
+        // wait for the table read; the read is still issued for every symbol and only consumed when slot >= c3.
         if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
             for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
                     const uint32_t slot8 = (x << 3) & ((kProbScale - 1) << 3);     // byte offset of ent[slot]
+                    const uint32_t slot = x & (kProbScale - 1);
                     const uint32_t xs = x >> kProbBits;
                     const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
                     slots[g * 16 + b] = (uint16_t)slot8;
-                    x = e.x * xs + e.y;
+                    const bool p1 = slot >= c1, p2 = slot >= c2;
+                    uint32_t f = p1 ? f1 : f0, cm = p1 ? c1 : 0u;
+                    f = p2 ? f2 : f;
+                    cm = p2 ? c2 : cm;
+                    x = f * xs + (slot - cm);
+                    if (slot >= c3) x = e.x * xs + e.y;       // rarer symbols: the table entry
                     // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
                     const bool ka = x < kRansL, kb = x < (1u << 15);
-                    uint32_t sa = ka ? 8u : 0u;
-                    sa = kb ? 16u : sa;
+                    const uint32_t sa = ka ? 8u : 0u;
                     x = __funnelshift_l(v, x, sa);
                     v = __funnelshift_l(lo, v, sa);
                     wa += sa;                                 // 8 address bytes per consumed stream byte
+                    if (kb) {                                 // second byte: only after a symbol with freq < 16
+                        const uint32_t lo2 = smem_ld_u32<4>(wa);
+                        x = __funnelshift_l(v, x, 8);
+                        v = __funnelshift_l(lo2, v, 8);
+                        wa += 8;
+                    }
                 }
             }
         }

@@ -161,7 +161,8 @@ __global__ void ALICE_LAUNCH_BOUNDS(32, 1)
 k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ enc_all,
               unsigned long long *__restrict__ results) {
     __shared__ uint4 tab[256];                       // EncSym of every symbol
-    __shared__ uint4 st_a[kEncBlock];                // staged per symbol of the block: {x_lim, rcp, cmpl, cum}
+    // staged per symbol of the block, indexed [b][lane] (symbol b of lane's group): conflict-free for the lanes
+    __shared__ uint4 st_a[kEncBlock];                // {x_lim, rcp, cmpl, cum}
     __shared__ uint32_t st_s[kEncBlock];             // division shift sh | (freq <= 16) << 8
     __shared__ uint32_t st_x[kEncBlock];             // state before the step of each symbol
     __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
@@ -229,9 +230,9 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             for (int b = 0; b < 16; b++) {
                 const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
                 const uint4 t = tab[sy];
-                st_sym[lane * 16 + b] = (uint8_t)sy;
-                st_a[lane * 16 + b] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_s[lane * 16 + b] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
+                st_sym[b * 32 + lane] = (uint8_t)sy;
+                st_a[b * 32 + lane] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
+                st_s[b * 32 + lane] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
                 fl |= t.w >> 24;
             }
             grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
@@ -247,7 +248,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             uint4 ea[16];
             uint32_t es[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) { ea[b] = st_a[31 * 16 + b]; es[b] = st_s[31 * 16 + b]; }
+            for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + 31]; es[b] = st_s[b * 32 + 31]; }
             uint32_t g = grp[31];
             for (int c = 31; c >= 0; c--) {
                 const int cn = c > 0 ? c - 1 : 0;
@@ -257,7 +258,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                     // computed and selected at the end, so the comparison is off the critical path.
 #pragma unroll
                     for (int b = 15; b >= 0; b--) {
-                        st_x[c * 16 + b] = x;
+                        st_x[b * 32 + c] = x;
                         const bool k = x > ea[b].x;
                         const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
                         const uint32_t sh = es[b];
@@ -265,14 +266,14 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         // floor(floor(x/f) / 256) == floor((x >> 8) / f)
                         const uint32_t xb = (hi >> (sh + 8u)) * ea[b].z + ((x >> 8) + ea[b].w);
                         x = k ? xb : xa;
-                        ea[b] = st_a[cn * 16 + b];
-                        es[b] = st_s[cn * 16 + b];
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
                     }
                 } else if (!(g & kGrpGeneric)) {
                     // some freq in [2, 16]: up to two renormalisation bytes
 #pragma unroll
                     for (int b = 15; b >= 0; b--) {
-                        st_x[c * 16 + b] = x;
+                        st_x[b * 32 + c] = x;
                         const uint32_t lim = ea[b].x;
                         const uint32_t lim2 = (es[b] & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
                         const uint32_t sh = es[b] & 0xffu;
@@ -281,13 +282,13 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         uint32_t sx = k1 ? 8u : 0u;
                         sx = k2 ? 16u : sx;
                         x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
-                        ea[b] = st_a[cn * 16 + b];
-                        es[b] = st_s[cn * 16 + b];
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
                     }
                 } else {
                     for (int b = 15; b >= 0; b--) {
-                        const uint4 e = tab[st_sym[c * 16 + b]];
-                        st_x[c * 16 + b] = x;
+                        const uint4 e = tab[st_sym[b * 32 + c]];
+                        st_x[b * 32 + c] = x;
                         if (e.w & kEncZero) { status |= 2u; continue; }
                         while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
                         const uint32_t f = kProbScale - e.z;
@@ -295,7 +296,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         x = x + (e.w & 0xffffu) + q * e.z;
                     }
 #pragma unroll
-                    for (int b = 0; b < 16; b++) { ea[b] = st_a[cn * 16 + b]; es[b] = st_s[cn * 16 + b]; }
+                    for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
                 }
                 g = gn;
             }
@@ -310,7 +311,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             uint32_t kb1 = 0, kb2 = 0;   // bit b: symbol b of my group emitted a first / second byte
 #pragma unroll
             for (int b = 0; b < 16; b++) {
-                const uint32_t sx = st_x[lane * 16 + b], lim = st_a[lane * 16 + b].x;
+                const uint32_t sx = st_x[b * 32 + lane], lim = st_a[b * 32 + lane].x;
                 kb1 |= (sx > lim ? 1u : 0u) << b;
                 kb2 |= ((sx > lim) && ((sx >> 8) > lim) ? 1u : 0u) << b;
             }
@@ -326,7 +327,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             uint32_t pos = sp - (incl - mine);          // my first byte goes to ring[pos - 1]
 #pragma unroll
             for (int b = 15; b >= 0; b--) {
-                const uint32_t sx = st_x[lane * 16 + b];
+                const uint32_t sx = st_x[b * 32 + lane];
                 if (kb1 & (1u << b)) ring[--pos] = (uint8_t)sx;
                 if (kb2 & (1u << b)) ring[--pos] = (uint8_t)(sx >> 8);
             }
@@ -425,24 +426,6 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         s.pos = 4;
     }
     const bool fast_ok = aux.wide_reachable == 0;
-    // register-resident decode of symbols 0..2 (slot ranges [0,c1), [c1,c2), [c2,c3)); empty ranges if the table
-    // does not start that way
-    uint32_t f0 = 1, f1 = 1, f2 = 1, c1 = 0, c2 = 0, c3 = 0;
-    if (symt[0] == 0 && ent[0].y == 0 && aux.wide_sym != 0) {
-        f0 = ent[0].x;
-        c1 = f0 < kProbScale ? f0 : kProbScale;
-        c2 = c3 = c1;
-        if (c1 < kProbScale && symt[c1] == 1 && ent[c1].y == 0 && aux.wide_sym != 1) {
-            f1 = ent[c1].x;
-            c2 = c1 + f1 < kProbScale ? c1 + f1 : kProbScale;
-            c3 = c2;
-            if (c2 < kProbScale && symt[c2] == 2 && ent[c2].y == 0 && aux.wide_sym != 2) {
-                f2 = ent[c2].x;
-                c3 = c2 + f2 < kProbScale ? c2 + f2 : kProbScale;
-            }
-        }
-    }
-
     // window ring over byte offsets relative to the 16-byte aligned address below job.in
     const uintptr_t in_addr = reinterpret_cast<uintptr_t>(job.in);
     const uint8_t *ga = reinterpret_cast<const uint8_t *>(in_addr & ~(uintptr_t)15);
@@ -521,38 +504,25 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
         const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
         smem_addr_t wa = wa0;                                 // running window address: 8 bytes per stream byte
-        // ---- lane 0 only (one active lane: every shared access is a single wavefront).  Symbols 0, 1 and 2 own the
-        // slot ranges [0,c1), [c1,c2), [c2,c3): their {freq, cum} live in registers, so the common symbols do not
-        // wait for the table read; the read is still issued for every symbol and only consumed when slot >= c3.
+        // ---- lane 0 only (one active lane: every shared access is a single wavefront)
         if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
             for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
                     const uint32_t slot8 = (x << 3) & ((kProbScale - 1) << 3);     // byte offset of ent[slot]
-                    const uint32_t slot = x & (kProbScale - 1);
                     const uint32_t xs = x >> kProbBits;
                     const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
                     slots[g * 16 + b] = (uint16_t)slot8;
-                    const bool p1 = slot >= c1, p2 = slot >= c2;
-                    uint32_t f = p1 ? f1 : f0, cm = p1 ? c1 : 0u;
-                    f = p2 ? f2 : f;
-                    cm = p2 ? c2 : cm;
-                    x = f * xs + (slot - cm);
-                    if (slot >= c3) x = e.x * xs + e.y;       // rarer symbols: the table entry
+                    x = e.x * xs + e.y;
                     // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
                     const bool ka = x < kRansL, kb = x < (1u << 15);
-                    const uint32_t sa = ka ? 8u : 0u;
+                    uint32_t sa = ka ? 8u : 0u;
+                    sa = kb ? 16u : sa;
                     x = __funnelshift_l(v, x, sa);
                     v = __funnelshift_l(lo, v, sa);
                     wa += sa;                                 // 8 address bytes per consumed stream byte
-                    if (kb) {                                 // second byte: only after a symbol with freq < 16
-                        const uint32_t lo2 = smem_ld_u32<4>(wa);
-                        x = __funnelshift_l(v, x, 8);
-                        v = __funnelshift_l(lo2, v, 8);
-                        wa += 8;
-                    }
                 }
             }
         }

@@ -25,41 +25,43 @@
 namespace alice {
 
 // ------------------------------------------------------------------------------ k_fwd_xy
-template <int M> struct RowPx { int r[2 * M], g[2 * M], b[2 * M]; };
+// Raw RGB of one lane's 2M pixels of one row, as 3M/2 little-endian words (byte 3i = R of pixel i, ...).
+template <int M> struct RowRaw { uint32_t w[3 * M / 2]; };
 
-template <int M>
-ALICE_D void load_row_rgb(const uint8_t *__restrict__ row, int x0, int w, bool vec_ok, RowPx<M> &px) {
+// EDGE = false: the caller guarantees 0 <= x0, x0 + 2M <= w and 4-byte alignment -> plain 32-bit loads.
+template <int M, bool EDGE>
+ALICE_D void load_row_raw(const uint8_t *__restrict__ row, int x0, int w, bool vec_ok, RowRaw<M> &raw) {
     constexpr int PXL = 2 * M;
-    if (vec_ok && x0 >= 0 && x0 + PXL <= w) {
-        static_assert((PXL * 3) % 4 == 0, "PXL*3 must be a multiple of 4");
-        constexpr int NW = PXL * 3 / 4;
+    static_assert((PXL * 3) % 4 == 0, "PXL*3 must be a multiple of 4");
+    constexpr int NW = PXL * 3 / 4;
+    if (!EDGE || (vec_ok && x0 >= 0 && x0 + PXL <= w)) {
         const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * 3);
-        uint32_t wd[NW];
 #pragma unroll
-        for (int i = 0; i < NW; i++) wd[i] = __ldg(p + i);
-#pragma unroll
-        for (int i = 0; i < PXL; i++) {
-            px.r[i] = (wd[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 0xff;
-            px.g[i] = (wd[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 0xff;
-            px.b[i] = (wd[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 0xff;
-        }
+        for (int i = 0; i < NW; i++) raw.w[i] = __ldg(p + i);
     } else {
+#pragma unroll
+        for (int i = 0; i < NW; i++) raw.w[i] = 0;
 #pragma unroll
         for (int i = 0; i < PXL; i++) {
             int x = x0 + i;
             x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);  // replicate-pad (pipeline.rs:95-98)
             const uint8_t *p = row + (size_t)x * 3;
-            px.r[i] = __ldg(p);
-            px.g[i] = __ldg(p + 1);
-            px.b[i] = __ldg(p + 2);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) raw.w[(3 * i + ch) >> 2] |= (uint32_t)__ldg(p + ch) << (8 * ((3 * i + ch) & 3));
         }
     }
 }
 
-template <int M>
+template <int M, bool EDGE>
 ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, int limit, bool lane_ok) {
     // M consecutive coefficients at columns xp .. xp+M-1, valid while column < limit.
-    if (!lane_ok || xp < 0) return;
+    if (!lane_ok) return;
+    if (!EDGE) {
+        static_assert(M == 2, "fast store assumes two coefficients per group");
+        *reinterpret_cast<uint32_t *>(dst + xp) = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+        return;
+    }
+    if (xp < 0) return;
     if (M == 2 && xp + 2 <= limit && ((reinterpret_cast<uintptr_t>(dst + xp) & 3) == 0)) {
         uint32_t pk = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
         *reinterpret_cast<uint32_t *>(dst + xp) = pk;
@@ -70,12 +72,113 @@ ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, in
         if (xp + i < limit) dst[xp + i] = (int16_t)v[i];
 }
 
-template <int WT, int M>
-__global__ void ALICE_LAUNCH_BOUNDS(128, 3)
-k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, int h, int f, int pw, int ph,
-         int n_strips, int n_segs, int seg_pairs, int vec_ok) {
+// One column strip of one frame, rows [i0, i1) of the y-transformed output.  EDGE = false: the strip touches neither
+// the left nor the right image border, every access is in range and aligned.
+template <int WT, int M, bool EDGE>
+ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict__ out_t, size_t plane_sz, int w, int h,
+                          int pw, int p0, int i0, int i1, int lane, bool vec_ok) {
     constexpr int NST = WaveletTraits<WT>::NST;
     constexpr int PXL = 2 * M;
+    const int halfx = pw >> 1, halfy = (h + (h & 1)) >> 1;
+    const int x0 = 2 * p0;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const int js = max(0, i0 - NST);
+    const int je = min(halfy, i1 + NST);
+
+    FwdLift<WT, false> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
+
+    auto load_pair = [&](int j, RowRaw<M> (&raw)[2]) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int y = min(2 * j + r, h - 1);  // replicate-pad the extra row (pipeline.rs:100-105)
+            load_row_raw<M, EDGE>(frame + (size_t)y * w * 3, x0, w, vec_ok, raw[r]);
+        }
+    };
+    // colour transform + x lifting of one row: v[c][0..M) = low-x, v[c][M..2M) = high-x
+    auto row_x = [&](const RowRaw<M> &raw, int (&v)[3][PXL]) {
+        int e[3][M], o[3][M];
+#pragma unroll
+        for (int i = 0; i < PXL; i++) {
+            const int r = (raw.w[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 0xff;
+            const int g = (raw.w[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 0xff;
+            const int bb = (raw.w[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 0xff;
+            // color.rs:221-232 (values fit i16, so i32 arithmetic is identical)
+            const int co = r - bb;
+            const int tt = bb + (co >> 1);
+            const int cg = g - tt;
+            const int yy = tt + (cg >> 1);
+            if (i & 1) { o[0][i >> 1] = yy; o[1][i >> 1] = co; o[2][i >> 1] = cg; }
+            else       { e[0][i >> 1] = yy; e[1][i >> 1] = co; e[2][i >> 1] = cg; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            fwd_lanes<WT, false, M, EDGE>(e[c], o[c], p0, halfx);
+#pragma unroll
+            for (int i = 0; i < M; i++) { v[c][i] = e[c][i]; v[c][M + i] = o[c][i]; }
+        }
+    };
+    auto emit = [&](int jo, const int (&lo)[3][PXL], const int (&hi)[3][PXL]) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int16_t *row_lo = out_t + c * plane_sz + (size_t)jo * pw;
+            int16_t *row_hi = out_t + c * plane_sz + (size_t)(halfy + jo) * pw;
+            store_group_i16<M, EDGE>(row_lo, &lo[c][0], p0, halfx, lane_ok);
+            store_group_i16<M, EDGE>(row_lo + halfx, &lo[c][M], p0, halfx, lane_ok);
+            store_group_i16<M, EDGE>(row_hi, &hi[c][0], p0, halfx, lane_ok);
+            store_group_i16<M, EDGE>(row_hi + halfx, &hi[c][M], p0, halfx, lane_ok);
+        }
+    };
+
+    RowRaw<M> cur[2], nxt[2];
+    if (js < je) load_pair(js, cur);
+    // warm-up and top-edge rows: the general streaming step (outputs before i0 are inexact and skipped)
+    const int j_main = min(je, max(js + NST + 1, i0 + NST));
+    int k = 0, j = js;
+    for (; j < j_main; j++, k++) {
+        if (j + 1 < je) load_pair(j + 1, nxt);
+        int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];
+        row_x(cur[0], v0);
+        row_x(cur[1], v1);
+        bool has = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) has = L[c][i].push(v0[c][i], v1[c][i], k, j, lo[c][i], hi[c][i]);
+        if (has && j - NST >= i0 && j - NST < i1) emit(j - NST, lo, hi);
+        cur[0] = nxt[0]; cur[1] = nxt[1];
+    }
+    // steady state: the next row pair is already in flight while this one is transformed
+    for (; j < je; j++, k++) {
+        load_pair(min(j + 1, je - 1), nxt);
+        int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];
+        row_x(cur[0], v0);
+        row_x(cur[1], v1);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) L[c][i].push_steady(v0[c][i], v1[c][i], lo[c][i], hi[c][i]);
+        emit(j - NST, lo, hi);
+        cur[0] = nxt[0]; cur[1] = nxt[1];
+    }
+    if (je == halfy && k > 0) {
+#pragma unroll
+        for (int which = 0; which < NST; which++) {
+            int lo[3][PXL], hi[3][PXL];
+            bool has = false;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int i = 0; i < PXL; i++) has = L[c][i].flush(k, which, halfy, lo[c][i], hi[c][i]);
+            const int jo = halfy - NST + which;
+            if (has && jo >= i0 && jo < i1) emit(jo, lo, hi);
+        }
+    }
+}
+
+template <int WT, int M>
+__global__ void ALICE_LAUNCH_BOUNDS(128, (WT == WT_CDF97 ? 2 : 3))
+k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, int h, int f, int pw, int ph,
+         int n_strips, int n_segs, int seg_pairs, int vec_ok) {
     constexpr int VPAIRS = 30 * M;
     const int lane = threadIdx.x & 31;
     const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -86,77 +189,15 @@ k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, i
     const int t = (int)(warp_g / ((long long)n_strips * n_segs));
     const int halfx = pw >> 1, halfy = ph >> 1;
     const int p0 = sx * VPAIRS - M + lane * M;
-    const int x0 = 2 * p0;
-    const bool lane_ok = lane >= 1 && lane <= 30;
     const int i0 = sg * seg_pairs;
     const int i1 = min(halfy, i0 + seg_pairs);
-    const int js = max(0, i0 - NST);
-    const int je = min(halfy, i1 + NST);
-
-    FwdLift<WT, false> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
     const uint8_t *frame = rgb + (size_t)t * w * h * 3;
     const size_t plane_sz = (size_t)f * ph * pw;
     int16_t *out_t = planes + (size_t)t * ph * pw;
-
-    auto emit = [&](int jo, const int (&lo)[3][PXL], const int (&hi)[3][PXL]) {
-        if (jo < i0 || jo >= i1) return;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int16_t *row_lo = out_t + c * plane_sz + (size_t)jo * pw;
-            int16_t *row_hi = out_t + c * plane_sz + (size_t)(halfy + jo) * pw;
-            store_group_i16<M>(row_lo, &lo[c][0], p0, halfx, lane_ok);
-            store_group_i16<M>(row_lo + halfx, &lo[c][M], p0, halfx, lane_ok);
-            store_group_i16<M>(row_hi, &hi[c][0], p0, halfx, lane_ok);
-            store_group_i16<M>(row_hi + halfx, &hi[c][M], p0, halfx, lane_ok);
-        }
-    };
-
-    int k = 0;
-    for (int j = js; j < je; j++, k++) {
-        int v[2][3][PXL];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            int y = min(2 * j + r, h - 1);  // replicate-pad the extra row (pipeline.rs:100-105)
-            RowPx<M> px;
-            load_row_rgb<M>(frame + (size_t)y * w * 3, x0, w, vec_ok != 0, px);
-            int e[3][M], o[3][M];
-#pragma unroll
-            for (int i = 0; i < PXL; i++) {
-                // color.rs:221-232 (values fit i16, so i32 arithmetic is identical)
-                int co = px.r[i] - px.b[i];
-                int tt = px.b[i] + (co >> 1);
-                int cg = px.g[i] - tt;
-                int yy = tt + (cg >> 1);
-                if (i & 1) { o[0][i >> 1] = yy; o[1][i >> 1] = co; o[2][i >> 1] = cg; }
-                else       { e[0][i >> 1] = yy; e[1][i >> 1] = co; e[2][i >> 1] = cg; }
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                fwd_lanes<WT, false, M>(e[c], o[c], p0, halfx);
-#pragma unroll
-                for (int i = 0; i < M; i++) { v[r][c][i] = e[c][i]; v[r][c][M + i] = o[c][i]; }
-            }
-        }
-        int lo[3][PXL], hi[3][PXL];
-        bool has = false;
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int i = 0; i < PXL; i++) has = L[c][i].push(v[0][c][i], v[1][c][i], k, j, lo[c][i], hi[c][i]);
-        if (has) emit(j - NST, lo, hi);
-    }
-    if (je == halfy) {
-#pragma unroll
-        for (int which = 0; which < NST; which++) {
-            int lo[3][PXL], hi[3][PXL];
-            bool has = false;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int i = 0; i < PXL; i++) has = L[c][i].flush(k, which, halfy, lo[c][i], hi[c][i]);
-            if (has) emit(halfy - NST + which, lo, hi);
-        }
-    }
+    // interior strip: no lane owns pair 0 or pair halfx-1 (the mirrored ones), all 32 lanes read inside the row
+    const bool interior = vec_ok && sx > 0 && (sx + 1) * VPAIRS + M <= halfx - 1 && (pw == w) && ((pw & 3) == 0);
+    if (interior) fwd_xy_strip<WT, M, false>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, true);
+    else fwd_xy_strip<WT, M, true>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, vec_ok != 0);
 }
 
 // ------------------------------------------------------------------------- k_fwd_t_quant
@@ -166,16 +207,17 @@ struct QuantDev {
 };
 
 ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
-    // Quantizer::quantize (quant.rs:89-97) with step >= 1, then to_symbols (quant.rs:555-560).
-    uint32_t a = (uint32_t)(v < 0 ? -v : v);
-    if ((int)a < q.dz) return 0;
-    uint32_t n = a - (uint32_t)q.half_dz;
-    uint32_t qa = q.step == 1 ? n : __umulhi(n, q.magic);  // exact: n < 2^26, step <= 64
-    if (qa == 0) return 0;
-    return (v > 0 ? 2 * qa - 1 : 2 * qa) & 0xff;
+    // Quantizer::quantize (quant.rs:89-97) with dead_zone == step >= 1, then to_symbols (quant.rs:555-560),
+    // without branches: for |v| < step the numerator |v| - step/2 is below step, so clamping it at 0 gives the
+    // dead zone; the symbol 2q-1 (v > 0) / 2q (v < 0) is max(2q - 1 - (v >> 31), 0) because q == 0 when v == 0.
+    const int a = v < 0 ? -v : v;
+    const int n = max(a - q.half_dz, 0);
+    const uint32_t qa = q.step == 1 ? (uint32_t)n : __umulhi((uint32_t)n, q.magic);   // exact: n < 2^26, magic = ceil(2^32/step)
+    const int s = max((int)(2u * qa) - 1 - (v >> 31), 0);
+    return (uint32_t)s & 0xffu;
 }
 
-template <int WT, int VEC>
+template <int WT, int VEC, int PF>
 __global__ void ALICE_LAUNCH_BOUNDS(256, 4)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
               int pw, int ph, int f, int pf, QuantDev q, int32_t *__restrict__ coef_dump) {
@@ -185,12 +227,11 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
 
-    const int halft = pf >> 1;
+    const int halft = PF ? PF / 2 : (pf >> 1);   // PF != 0: compile-time depth, the streaming state machine unrolls away
     const size_t frame_sz = (size_t)ph * pw;
     const int16_t *src = planes + (size_t)c * f * frame_sz;
     uint8_t *dst = symbols + (size_t)c * pf * frame_sz;
     const long long n_items = (long long)(frame_sz / VEC);
-    unsigned zeros = 0;
 
     auto emit = [&](size_t off, int jo, const int (&lo)[VEC], const int (&hi)[VEC]) {
         uint32_t pl = 0, phh = 0;
@@ -199,8 +240,8 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
             uint32_t sl = quant_symbol(lo[i], q), sh = quant_symbol(hi[i], q);
             pl |= sl << (8 * i);
             phh |= sh << (8 * i);
-            if (sl) atomicAdd(&sh_hist[sl], 1u); else zeros++;
-            if (sh) atomicAdd(&sh_hist[sh], 1u); else zeros++;
+            if (sl) atomicAdd(&sh_hist[sl], 1u);   // bin 0 is filled in afterwards: N - sum of the others
+            if (sh) atomicAdd(&sh_hist[sh], 1u);
         }
         if (coef_dump) {  // parity-test stage dump of the 3-D coefficients (null in production)
             int32_t *cd = coef_dump + (size_t)c * pf * frame_sz;
@@ -226,6 +267,7 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
         const size_t off = (size_t)item * VEC;
         FwdLift<WT, false> L[VEC];
         int k = 0;
+#pragma unroll
         for (int j = 0; j < halft; j++, k++) {
             const int t0 = min(2 * j, f - 1), t1 = min(2 * j + 1, f - 1);  // pipeline.rs:107-112
             int e[VEC], o[VEC];
@@ -260,13 +302,19 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
         }
     }
 
-    // zero symbols are counted in a register and folded in once per warp
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) zeros += __shfl_xor_sync(kFullMask, zeros, s);
-    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(&sh_hist[0], zeros);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         if (sh_hist[i]) atomicAdd(&hist[c * 256 + i], sh_hist[i]);
+}
+
+// bin 0 = number of symbols - sum of the other bins (the kernels above only count non-zero symbols)
+__global__ void k_hist_zero_bin(unsigned *__restrict__ hist, unsigned n_symbols) {
+    unsigned *h = hist + blockIdx.x * 256;
+    unsigned s = 0;
+    for (int i = 1 + threadIdx.x; i < 256; i += 32) s += h[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+    if (threadIdx.x == 0) h[0] = n_symbols - s;
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -296,17 +344,21 @@ static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbo
     q.half_dz = step / 2;
     q.magic = step >= 2 ? (uint32_t)((((uint64_t)1 << 32) + step - 1) / step) : 0;
     const size_t frame_sz = (size_t)pw * ph;
-    if (pw % 4 == 0) {
-        long long items = frame_sz / 4;
-        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
-        auto kt = k_fwd_t_quant<WT, 4>;
-        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
+    const int vec = (pw % 4 == 0) ? 4 : 2;
+    const long long items = frame_sz / vec;
+    const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+    const dim3 tgrid(gx, 1, 3), block(256);
+    if (vec == 4 && pf == 64) {
+        auto kt = k_fwd_t_quant<WT, 4, 64>;
+        ALICE_LAUNCH(kt, tgrid, block, 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
+    } else if (vec == 4) {
+        auto kt = k_fwd_t_quant<WT, 4, 0>;
+        ALICE_LAUNCH(kt, tgrid, block, 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
     } else {
-        long long items = frame_sz / 2;
-        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
-        auto kt = k_fwd_t_quant<WT, 2>;
-        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
+        auto kt = k_fwd_t_quant<WT, 2, 0>;
+        ALICE_LAUNCH(kt, tgrid, block, 0, st, d_planes, d_symbols, d_hist, pw, ph, f, pf, q, d_coef_dump);
     }
+    ALICE_LAUNCH(k_hist_zero_bin, dim3(3), dim3(32), 0, st, d_hist, (unsigned)((size_t)pf * frame_sz));
 }
 
 void forward_frontend(int wavelet, const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist,

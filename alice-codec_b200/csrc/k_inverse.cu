@@ -28,14 +28,14 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
     return (int)((unsigned)q * (unsigned)step);
 }
 
-template <int WT, int VEC>
+template <int WT, int VEC, int PF>
 __global__ void ALICE_LAUNCH_BOUNDS(256, 4)
 k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw, int ph, int f, int pf, int step0,
         int step1, int step2) {
     constexpr int NST = WaveletTraits<WT>::NST;
     const int c = blockIdx.z;
     const int step = c == 0 ? step0 : (c == 1 ? step1 : step2);
-    const int halft = pf >> 1;
+    const int halft = PF ? PF / 2 : (pf >> 1);   // PF != 0: compile-time depth, the streaming state machine unrolls away
     const size_t frame_sz = (size_t)ph * pw;
     const uint8_t *src = symbols + (size_t)c * pf * frame_sz;
     int32_t *dst = coef + (size_t)c * f * frame_sz;
@@ -60,6 +60,7 @@ k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw,
         const size_t off = (size_t)item * VEC;
         InvLift<WT, true> L[VEC];
         int k = 0;
+#pragma unroll
         for (int j = 0; j < halft; j++, k++) {
             uint32_t a, b;
             if (VEC == 4) {
@@ -225,18 +226,21 @@ template <int WT>
 static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f, int pw, int ph,
                        int pf, const int steps[3], cudaStream_t st) {
     const size_t frame_sz = (size_t)pw * ph;
-    if (pw % 4 == 0) {
-        long long items = frame_sz / 4;
-        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
-        auto kt = k_inv_t<WT, 4>;
-        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1],
-                     steps[2]);
-    } else {
-        long long items = frame_sz / 2;
-        unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
-        auto kt = k_inv_t<WT, 2>;
-        ALICE_LAUNCH(kt, dim3(gx, 1, 3), dim3(256), 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1],
-                     steps[2]);
+    {
+        const int vec = (pw % 4 == 0) ? 4 : 2;
+        const long long items = frame_sz / vec;
+        const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        const dim3 tgrid(gx, 1, 3), tblock(256);
+        if (vec == 4 && pf == 64) {
+            auto kt = k_inv_t<WT, 4, 64>;
+            ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
+        } else if (vec == 4) {
+            auto kt = k_inv_t<WT, 4, 0>;
+            ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
+        } else {
+            auto kt = k_inv_t<WT, 2, 0>;
+            ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
+        }
     }
     constexpr int M = 2;
     const int halfx = pw / 2, halfy = ph / 2;

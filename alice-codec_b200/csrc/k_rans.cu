@@ -507,10 +507,11 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         // ---- lane 0 only (one active lane: every shared access is a single wavefront)
         if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
+            uint32_t x3 = x << 3;                             // the state shifted by 3: its low bits address ent[]
             for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
-                    const uint32_t slot8 = (x << 3) & ((kProbScale - 1) << 3);     // byte offset of ent[slot]
+                    const uint32_t slot8 = x3 & ((kProbScale - 1) << 3);           // byte offset of ent[slot]
                     const uint32_t xs = x >> kProbBits;
                     const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
@@ -518,8 +519,10 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
                     x = e.x * xs + e.y;
                     // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
                     const bool ka = x < kRansL, kb = x < (1u << 15);
-                    uint32_t sa = ka ? 8u : 0u;
+                    uint32_t sa = ka ? 8u : 0u, sa3 = ka ? 11u : 3u;
                     sa = kb ? 16u : sa;
+                    sa3 = kb ? 19u : sa3;
+                    x3 = __funnelshift_l(v, x, sa3);          // (renormalised x) << 3, without waiting for it
                     x = __funnelshift_l(v, x, sa);
                     v = __funnelshift_l(lo, v, sa);
                     wa += sa;                                 // 8 address bytes per consumed stream byte

@@ -76,6 +76,18 @@ template <int WT, bool WIDE> struct FwdLift {
         lo = s2; hi = dd;
         return true;
     }
+    // push() for k > NST and j > NST: no warm-up and no left-edge mirror, the pair j-NST always comes out
+    ALICE_HD void push_steady(int en, int on, int &lo, int &hi) {
+        const int d_old = d;
+        int s1, d1;
+        stage(e, o, en, d, false, coef_p<WT>(0), coef_u<WT>(0), s1, d1);
+        d = d1; e = en; o = on;
+        if (NST == 1) { lo = s1; hi = d1; return; }
+        int s2, dd;
+        stage(e2, d_old, s1, d2, false, coef_p<WT>(1), coef_u<WT>(1), s2, dd);
+        d2 = dd; e2 = s1;
+        lo = s2; hi = dd;
+    }
     // which = 0 .. NST-1; half = number of pairs in the whole line; k = pairs pushed so far (>= 1).
     ALICE_HD bool flush(int k, int which, int half, int &lo, int &hi) {
         if (NST == 1) {
@@ -154,7 +166,8 @@ template <int WT, bool WIDE> struct InvLift {
 // `half` pairs.  On return e[] holds the low-pass and o[] the high-pass values of those
 // pairs.  Exact for lanes 1..30 (M >= 2); lanes 0 / 31 are halo lanes.
 // ---------------------------------------------------------------------------------------
-template <int WT, bool WIDE, int M> ALICE_D void fwd_lanes(int (&e)[M], int (&o)[M], int p0, int half) {
+template <int WT, bool WIDE, int M, bool EDGE = true>
+ALICE_D void fwd_lanes(int (&e)[M], int (&o)[M], int p0, int half) {
 #pragma unroll
     for (int st = 0; st < WaveletTraits<WT>::NST; st++) {
         const int cp = coef_p<WT>(st), cu = coef_u<WT>(st);
@@ -162,21 +175,22 @@ template <int WT, bool WIDE, int M> ALICE_D void fwd_lanes(int (&e)[M], int (&o)
 #pragma unroll
         for (int k = 0; k < M; k++) {
             int er = (k + 1 < M) ? e[k + 1] : e_nb;
-            if (p0 + k == half - 1) er = e[k];                      // mirror at the right edge
+            if (EDGE && p0 + k == half - 1) er = e[k];              // mirror at the right edge
             o[k] = wadd(o[k], lift_delta<WIDE>(wadd(e[k], er), cp));
         }
         int d_nb = __shfl_up_sync(kFullMask, o[M - 1], 1);
 #pragma unroll
         for (int k = 0; k < M; k++) {
             int dl = (k > 0) ? o[k - 1] : d_nb;
-            if (p0 + k == 0) dl = o[k];                             // mirror at the left edge
+            if (EDGE && p0 + k == 0) dl = o[k];                     // mirror at the left edge
             e[k] = wadd(e[k], lift_delta<WIDE>(wadd(dl, o[k]), cu));
         }
     }
 }
 
 // Lane-parallel inverse along x: in: e[] = low[p0..], o[] = high[p0..]; out: e[] = s[2p], o[] = s[2p+1].
-template <int WT, bool WIDE, int M> ALICE_D void inv_lanes(int (&e)[M], int (&o)[M], int p0, int half) {
+template <int WT, bool WIDE, int M, bool EDGE = true>
+ALICE_D void inv_lanes(int (&e)[M], int (&o)[M], int p0, int half) {
 #pragma unroll
     for (int st = WaveletTraits<WT>::NST - 1; st >= 0; st--) {
         const int cp = coef_p<WT>(st), cu = coef_u<WT>(st);
@@ -184,14 +198,14 @@ template <int WT, bool WIDE, int M> ALICE_D void inv_lanes(int (&e)[M], int (&o)
 #pragma unroll
         for (int k = 0; k < M; k++) {
             int ol = (k > 0) ? o[k - 1] : o_nb;
-            if (p0 + k == 0) ol = o[k];
+            if (EDGE && p0 + k == 0) ol = o[k];
             e[k] = wadd(e[k], lift_delta<WIDE>(wadd(ol, o[k]), -cu));
         }
         int e_nb = __shfl_down_sync(kFullMask, e[0], 1);
 #pragma unroll
         for (int k = 0; k < M; k++) {
             int er = (k + 1 < M) ? e[k + 1] : e_nb;
-            if (p0 + k == half - 1) er = e[k];
+            if (EDGE && p0 + k == half - 1) er = e[k];
             o[k] = wadd(o[k], lift_delta<WIDE>(wadd(e[k], er), -cp));
         }
     }

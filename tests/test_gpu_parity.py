@@ -36,7 +36,7 @@ def test_survey_kats(api, row):
 
 
 SHAPES = [(1, 1, 1), (2, 2, 2), (3, 5, 1), (5, 3, 3), (7, 2, 4), (2, 9, 5), (1, 40, 7), (40, 1, 7), (66, 6, 2),
-          (130, 4, 2), (6, 70, 2), (12, 6, 64), (121, 67, 9), (124, 62, 64), (250, 30, 3), (64, 64, 65), (31, 33, 128)]
+          (130, 4, 2), (6, 70, 2), (12, 6, 64), (121, 67, 9), (124, 62, 64), (250, 30, 3), (64, 64, 65), (31, 33, 128), (256, 6, 2), (380, 10, 3), (260, 4, 64), (512, 270, 3)]
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))

@@ -22,22 +22,32 @@
 #include "kernels.h"
 #include "lifting.cuh"
 
+#ifndef ALICE_FWD_M
+#define ALICE_FWD_M 1   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
+#endif
+
 namespace alice {
 
 // ------------------------------------------------------------------------------ k_fwd_xy
 // Raw RGB of one lane's 2M pixels of one row, as 3M/2 little-endian words (byte 3i = R of pixel i, ...).
-template <int M> struct RowRaw { uint32_t w[3 * M / 2]; };
+template <int M> struct RowRaw { uint32_t w[(6 * M + 3) / 4]; };
 
-// EDGE = false: the caller guarantees 0 <= x0, x0 + 2M <= w and 4-byte alignment -> plain 32-bit loads.
+// EDGE = false: the caller guarantees 0 <= x0, x0 + 2M <= w and 4-byte alignment of the row -> plain loads.
 template <int M, bool EDGE>
 ALICE_D void load_row_raw(const uint8_t *__restrict__ row, int x0, int w, bool vec_ok, RowRaw<M> &raw) {
     constexpr int PXL = 2 * M;
-    static_assert((PXL * 3) % 4 == 0, "PXL*3 must be a multiple of 4");
-    constexpr int NW = PXL * 3 / 4;
+    constexpr int NB = PXL * 3;          // bytes per lane: 6 (M = 1) or 12 (M = 2)
+    constexpr int NW = (NB + 3) / 4;
     if (!EDGE || (vec_ok && x0 >= 0 && x0 + PXL <= w)) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * 3);
+        if (NB % 4 == 0) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * 3);
 #pragma unroll
-        for (int i = 0; i < NW; i++) raw.w[i] = __ldg(p + i);
+            for (int i = 0; i < NW; i++) raw.w[i] = __ldg(p + i);
+        } else {                         // 6 bytes at a 2-byte aligned address (x0 is even)
+            const uint16_t *p = reinterpret_cast<const uint16_t *>(row + (size_t)x0 * 3);
+            raw.w[0] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 16);
+            raw.w[1] = (uint32_t)__ldg(p + 2);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < NW; i++) raw.w[i] = 0;
@@ -57,8 +67,8 @@ ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, in
     // M consecutive coefficients at columns xp .. xp+M-1, valid while column < limit.
     if (!lane_ok) return;
     if (!EDGE) {
-        static_assert(M == 2, "fast store assumes two coefficients per group");
-        *reinterpret_cast<uint32_t *>(dst + xp) = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+        if (M == 2) *reinterpret_cast<uint32_t *>(dst + xp) = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[M - 1] << 16);
+        else dst[xp] = (int16_t)v[0];
         return;
     }
     if (xp < 0) return;
@@ -81,7 +91,8 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     constexpr int PXL = 2 * M;
     const int halfx = pw >> 1, halfy = (h + (h & 1)) >> 1;
     const int x0 = 2 * p0;
-    const bool lane_ok = lane >= 1 && lane <= 30;
+    constexpr int HL = (NST + M - 1) / M;     // halo lanes per side: a lane's result needs NST pairs on either side
+    const bool lane_ok = lane >= HL && lane < 32 - HL;
     const int js = max(0, i0 - NST);
     const int je = min(halfy, i1 + NST);
 
@@ -176,10 +187,11 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
 }
 
 template <int WT, int M>
-__global__ void ALICE_LAUNCH_BOUNDS(128, (WT == WT_CDF97 ? 2 : 3))
+__global__ void ALICE_LAUNCH_BOUNDS(128, (M == 1 ? 4 : (WT == WT_CDF97 ? 2 : 3)))
 k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, int h, int f, int pw, int ph,
          int n_strips, int n_segs, int seg_pairs, int vec_ok) {
-    constexpr int VPAIRS = 30 * M;
+    constexpr int HL = (WaveletTraits<WT>::NST + M - 1) / M;
+    constexpr int VPAIRS = (32 - 2 * HL) * M;
     const int lane = threadIdx.x & 31;
     const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long n_warps = (long long)n_strips * n_segs * f;
@@ -188,14 +200,14 @@ k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, i
     const int sg = (int)((warp_g / n_strips) % n_segs);
     const int t = (int)(warp_g / ((long long)n_strips * n_segs));
     const int halfx = pw >> 1, halfy = ph >> 1;
-    const int p0 = sx * VPAIRS - M + lane * M;
+    const int p0 = sx * VPAIRS - HL * M + lane * M;
     const int i0 = sg * seg_pairs;
     const int i1 = min(halfy, i0 + seg_pairs);
     const uint8_t *frame = rgb + (size_t)t * w * h * 3;
     const size_t plane_sz = (size_t)f * ph * pw;
     int16_t *out_t = planes + (size_t)t * ph * pw;
     // interior strip: no lane owns pair 0 or pair halfx-1 (the mirrored ones), all 32 lanes read inside the row
-    const bool interior = vec_ok && sx > 0 && (sx + 1) * VPAIRS + M <= halfx - 1 && (pw == w) && ((pw & 3) == 0);
+    const bool interior = vec_ok && sx > 0 && (sx + 1) * VPAIRS + HL * M <= halfx - 1 && (pw == w) && ((pw & 3) == 0);  // rows 4-byte aligned
     if (interior) fwd_xy_strip<WT, M, false>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, true);
     else fwd_xy_strip<WT, M, true>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, vec_ok != 0);
 }
@@ -321,9 +333,10 @@ __global__ void k_hist_zero_bin(unsigned *__restrict__ hist, unsigned n_symbols)
 template <int WT>
 static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist, int w, int h,
                        int f, int pw, int ph, int pf, int step, int32_t *d_coef_dump, cudaStream_t st) {
-    constexpr int M = 2;
+    constexpr int M = ALICE_FWD_M;
     const int halfx = pw / 2, halfy = ph / 2;
-    const int n_strips = (halfx + 30 * M - 1) / (30 * M);
+    constexpr int VPAIRS = (32 - 2 * ((WaveletTraits<WT>::NST + M - 1) / M)) * M;
+    const int n_strips = (halfx + VPAIRS - 1) / VPAIRS;
     // enough warps to fill the machine: aim for >= 148*24 warps, segments of >= 16 row pairs
     long long base_warps = (long long)n_strips * f;
     int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * 24 + base_warps - 1) / base_warps),

@@ -29,7 +29,7 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 }
 
 template <int WT, int VEC, int PF>
-__global__ void ALICE_LAUNCH_BOUNDS(256, 4)
+__global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 2 : 4))
 k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw, int ph, int f, int pf, int step0,
         int step1, int step2) {
     constexpr int NST = WaveletTraits<WT>::NST;
@@ -231,7 +231,7 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
         const long long items = frame_sz / vec;
         const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
         const dim3 tgrid(gx, 1, 3), tblock(256);
-        if (vec == 4 && pf == 64) {
+        if (false && vec == 4 && pf == 64) {   // full unrolling of the 64-bit lifting spills heavily: runtime loop is faster
             auto kt = k_inv_t<WT, 4, 64>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
         } else if (vec == 4) {

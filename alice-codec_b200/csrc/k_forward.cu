@@ -23,7 +23,7 @@
 #include "lifting.cuh"
 
 #ifndef ALICE_FWD_M
-#define ALICE_FWD_M 1   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
+#define ALICE_FWD_M 2   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
 #endif
 
 namespace alice {

@@ -5,7 +5,7 @@ The product is `lib/libalice_codec.so` (CUDA kernels + C ABI, built from `csrc/`
 interface on top of that C ABI.  The directory name carries a hyphen, so import it through
 `__graft_entry__.load_package()` (which registers it as `alice_codec_b200`).
 """
-from . import _capi  # noqa: F401
+from . import _capi, sharding  # noqa: F401
 from .api import (Api, ChunkBatch, CodecError, EncodedChunk, FrameDecoder, FrameEncoder, ReferenceAbi,  # noqa: F401
                   SUBBANDS, WAVELET_BYTES, WAVELET_NAMES, default_api)
 

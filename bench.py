@@ -10,10 +10,12 @@ hot path over a batch of B independent chunks per GPU:
     encode : RGB -> YCoCg-R -> 3-D lifting -> quantise -> symbols + histograms -> frequency tables -> 3B rANS lanes
     decode : tables -> 3B rANS lanes -> dequantise -> inverse lifting -> RGB
 `value`  = frames/s with the RGB inputs already resident in HBM (whole job, all GPUs).
-`e2e`    = the same metric through the C-ABI batch call with HOST buffers (pinned): H2D of every RGB chunk,
-           D2H of the .alc payloads, H2D of the payloads again for decode, D2H of every decoded RGB chunk.
-`roofline` = the encode front-end (the HBM-bound wavelet/quant stage the north-star targets): 6 algorithmic
-           bytes per pixel (3 in + 3 out) / its CUDA-event duration vs the measured HBM peak.
+`e2e`    = the same metric through the C-ABI batch calls with HOST buffers (pinned): H2D of every RGB chunk,
+           D2H of the .alc payloads, H2D of the payloads again for decode, D2H of every decoded RGB chunk; the
+           chunks are split over a few host threads, each with its own batch, so copies overlap the rANS kernels.
+`roofline` = the dominant kernel of the step by device time (a rANS launch); `roofline_by_kernel` lists all four
+           stages, incl. the wavelet/quantise front-end and back-end, whose algorithmic traffic is 6 B per pixel
+           (3 in + 3 out); achieved = algorithmic bytes / CUDA-event time, peak = measured HBM copy.
 `cpu_baseline` = the C oracle (a port of the reference's single-threaded CPU path) on this box's host.
 Multi-GPU: chunks are independent, so each rank runs its own batch (weak scaling), no collective on the data
 path; torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timed region.
@@ -150,7 +152,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=0, help="chunks in flight per GPU (0 = sized from free HBM)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (0 = same as --chunks)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--cpu-frames", type=int, default=32)
@@ -247,27 +249,54 @@ def main():
                 bit_exact = (hashlib.sha256(alc).hexdigest() == g["sha256_alc"] and
                              hashlib.sha256(d_out[0].cpu().numpy().tobytes()).hexdigest() == g["sha256_decoded"])
 
-    # ---- roofline of the HBM-bound front-end stage, from the library's own CUDA events on the launch stream
+    # ---- rooflines, from the library's own CUDA events on the launch stream (averaged over the timed steps).
+    # `roofline` describes the DOMINANT kernel of the step by device time (the rANS decode launch: one warp per
+    # (chunk, channel) stream, a serial recurrence); `roofline_by_kernel` lists every stage, including the
+    # wavelet/quantise front-end and back-end that the 6 B/px algorithmic HBM roofline is defined for.
     peak, peak_src = _peaks()
     fe_ms, be_ms = float(stage_ms[0]), float(stage_ms[5])
+    enc_ms, dec_ms = float(stage_ms[2]), float(stage_ms[4])
     alg_bytes = BYTES_PER_PX_ALG * n_px * B
-    achieved = alg_bytes / (fe_ms / 1000.0) / 1e9 if fe_ms > 0 else 0.0
     n_sym = 3 * n_px * B
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    roofline = {"bound": "hbm", "kernel": "encode front-end (k_fwd_xy + k_fwd_t_quant + k_hist_zero_bin per chunk, summed over the batch)",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms": round(fe_ms, 3),
-                "share_of_step": round(fe_ms / ms_step, 5)}
+    payload_bytes = 0
+    if rank == 0:
+        payload_bytes = sum(batch.get_chunk(i).compressed_size for i in range(min(B, 4))) / min(B, 4) * B
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and (args.quality, args.wavelet) == (QUALITY, WAVELET):
+        traffic = json.load(open(tp))
+
+    def rl(kernel, bytes_alg, ms, traffic_bytes=None, note=None):
+        ach = bytes_alg / (ms / 1000.0) / 1e9 if ms > 0 else 0.0
+        d = {"bound": "hbm", "kernel": kernel, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+             "frac": round(ach / peak, 4), "traffic": traffic_bytes, "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": bytes_alg, "ms": round(ms, 3), "share_of_step": round(ms / ms_step, 5)}
+        if note:
+            d["note"] = note
+        return d
+    by_kernel = {
+        "frontend": rl("encode front-end: k_fwd_xy + k_fwd_t_quant + k_hist_zero_bin per chunk, summed over the batch",
+                       alg_bytes, fe_ms, traffic.get("frontend_dram_bytes_per_chunk", 0) * B or None,
+                       "6 B/px algorithmic (3 in + 3 out); INT32-issue bound, see DESIGN.md 4.2"),
+        "backend": rl("decode back-end: k_inv_t + k_inv_yx per chunk, summed over the batch", alg_bytes, be_ms,
+                      traffic.get("backend_dram_bytes_per_chunk", 0) * B or None, "6 B/px algorithmic"),
+        "rans_encode": rl("k_rans_encode (one launch, 3 streams per chunk)", n_sym + payload_bytes, enc_ms, None,
+                          "serial recurrence per stream: latency bound, symbols/s per lane is the figure of merit"),
+        "rans_decode": rl("k_rans_decode (one launch, 3 streams per chunk)", n_sym + payload_bytes, dec_ms, None,
+                          "serial recurrence per stream: latency bound, symbols/s per lane is the figure of merit"),
+    }
+    dominant = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
+    roofline = dict(by_kernel[dominant])
+    roofline["dominant_of"] = {k: v["share_of_step"] for k, v in by_kernel.items()}
     stages = {"frontend_ms": round(fe_ms, 3), "tables_enc_ms": round(float(stage_ms[1]), 3),
-              "rans_encode_ms": round(float(stage_ms[2]), 3), "tables_dec_ms": round(float(stage_ms[3]), 3),
-              "rans_decode_ms": round(float(stage_ms[4]), 3), "backend_ms": round(be_ms, 3),
-              "backend_gbs_alg": round(alg_bytes / (be_ms / 1000.0) / 1e9, 1) if be_ms > 0 else None,
+              "rans_encode_ms": round(enc_ms, 3), "tables_dec_ms": round(float(stage_ms[3]), 3),
+              "rans_decode_ms": round(dec_ms, 3), "backend_ms": round(be_ms, 3),
               "rans_lanes": 3 * B,
-              "rans_encode_msym_s_per_lane": round(n_px / (stage_ms[2] / 1000.0) / 1e6, 2) if stage_ms[2] > 0 else None,
-              "rans_decode_msym_s_per_lane": round(n_px / (stage_ms[4] / 1000.0) / 1e6, 2) if stage_ms[4] > 0 else None,
-              "rans_encode_msym_s_per_sm": round(n_sym / (stage_ms[2] / 1000.0) / 1e6 / n_sm, 2) if stage_ms[2] > 0 else None,
-              "rans_decode_msym_s_per_sm": round(n_sym / (stage_ms[4] / 1000.0) / 1e6 / n_sm, 2) if stage_ms[4] > 0 else None}
+              "rans_encode_msym_s_per_lane": round(n_px / (enc_ms / 1000.0) / 1e6, 2) if enc_ms > 0 else None,
+              "rans_decode_msym_s_per_lane": round(n_px / (dec_ms / 1000.0) / 1e6, 2) if dec_ms > 0 else None,
+              "rans_encode_msym_s_per_sm": round(n_sym / (enc_ms / 1000.0) / 1e6 / n_sm, 2) if enc_ms > 0 else None,
+              "rans_decode_msym_s_per_sm": round(n_sym / (dec_ms / 1000.0) / 1e6 / n_sm, 2) if dec_ms > 0 else None}
 
     # ---- e2e: the same metric through the host-buffer C-ABI call, copies inside the timed region
     e2e = None
@@ -296,19 +325,20 @@ def main():
             hin = [h_in[i].data_ptr() for i in shares[t]]
             hout = [h_out[i].data_ptr() for i in shares[t]]
             for it in range(1 + args.e2e_steps):        # iteration 0 = warm-up (staging buffers, first-touch)
-                gate.wait()
+                if it < 2:
+                    gate.wait()                         # start of the warm-up / of the timed region
                 chunks = batches[t].encode_host(hin)    # H2D RGB, kernels, D2H headers + payload
                 payload[t] = sum(c.compressed_size + 3138 for c in chunks)
                 batches[t].decode_host(chunks, hout)    # H2D payload, kernels, D2H RGB
-                gate.wait()
+                if it == 0 or it == args.e2e_steps:
+                    gate.wait()                         # end of the warm-up / of the timed region
         threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
         for th in threads:
             th.start()
         gate.wait(); gate.wait()                        # warm-up iteration
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            gate.wait(); gate.wait()
+        gate.wait(); gate.wait()                        # the threads run their e2e_steps back to back, unsynchronised
         barrier()
         dt = time.perf_counter() - t0
         for th in threads:
@@ -344,7 +374,8 @@ def main():
                            "input": "G1 tri+hash volumes generated on the device, one seed per chunk",
                            "l2": "inputs (%.1f GB per step per GPU) are far larger than the 126 MB L2" % (B * rgb_bytes / 1e9),
                            "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective"},
-                "e2e": e2e, "gpu_launches": args.steps * (5 * B + 4), "roofline": roofline, "stages": stages,
+                "e2e": e2e, "gpu_launches": args.steps * (5 * B + 4), "roofline": roofline, "roofline_by_kernel": by_kernel,
+                "stages": stages,
                 "cpu_baseline": cpu, "clocks": sampler.summary(), "bit_exact_vs_oracle_digest": bit_exact}
         print(json.dumps(line), flush=True)
     if batch is not None:

@@ -606,9 +606,9 @@ AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t 
     if (!cuda_ready()) return nullptr;
     AliceBatch *b = new (std::nothrow) AliceBatch();
     if (!b) return nullptr;
-    // single chunks keep the worst-case payload capacity; batches budget N/2 + 64 KiB per stream and fall
+    // single chunks keep the worst-case payload capacity; batches budget N/3 + 64 KiB per stream and fall
     // back to a worst-case buffer for any stream that overflows (Engine::run_rans_encode)
-    const uint64_t cap = n_chunks == 1 ? 0 : d.padded / 2 + 65536;
+    const uint64_t cap = n_chunks == 1 ? 0 : d.padded / 3 + 65536;
     b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false);
     if (!b->eng || !b->eng->ok()) { delete b->eng; delete b; return nullptr; }
     b->quality = quality;

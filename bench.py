@@ -188,10 +188,10 @@ def main():
     n_px = W * H * F
     rgb_bytes = 3 * n_px
     free_b, total_b = torch.cuda.mem_get_info()
-    # per chunk in flight: RGB in + RGB out (bench buffers) + symbols (3 B/px) + payload budget (1.5 B/px + 192 KiB)
-    per_chunk = 2 * rgb_bytes + 3 * n_px + int(1.5 * n_px) + 3 * 65536 + 3 * (4096 + 256 * 16 + 1024)
+    # per chunk in flight: RGB in + RGB out (bench buffers) + symbols (3 B/px) + payload budget (1 B/px + 192 KiB)
+    per_chunk = 2 * rgb_bytes + 3 * n_px + n_px + 3 * 65536 + 3 * (16384 + 256 * 16 + 1024)
     fixed = 12 * n_px + (2 << 30)            # 4-byte scratch volume x 3 channels + head-room
-    B = args.chunks or max(1, min(96, int((free_b - fixed) // per_chunk)))
+    B = args.chunks or max(1, min(120, int((free_b - fixed) // per_chunk)))
     d_in = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
     d_out = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
     for i, t in enumerate(d_in):

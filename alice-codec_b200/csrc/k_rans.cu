@@ -163,7 +163,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
     __shared__ uint4 tab[256];                       // EncSym of every symbol
     // staged per symbol of the block, indexed [b][lane] (symbol b of lane's group): conflict-free for the lanes
     __shared__ uint4 st_a[kEncBlock];                // {x_lim, rcp, cmpl, cum}
-    __shared__ uint2 st_s[kEncBlock];                // {division shift sh | (freq <= 16) << 8, sh + 8}
+    __shared__ uint32_t st_s[kEncBlock];             // division shift sh | (freq <= 16) << 8
     __shared__ uint32_t st_x[kEncBlock];             // state before the step of each symbol
     __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
     __shared__ uint8_t st_sym[kEncBlock];            // the symbols themselves (generic path)
@@ -232,8 +232,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                 const uint4 t = tab[sy];
                 st_sym[b * 32 + lane] = (uint8_t)sy;
                 st_a[b * 32 + lane] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_s[b * 32 + lane] = make_uint2(((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u),
-                                                 ((t.w >> 16) & 0xffu) + 8u);
+                st_s[b * 32 + lane] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
                 fl |= t.w >> 24;
             }
             grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
@@ -245,68 +244,61 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
         // serial code has no stream pointer to maintain.  (One active lane also makes every 16-byte shared load a
         // single wavefront.)  Entries of the next group are loaded into each register slot as soon as the
         // current group has used it, so the loads issue in the shadow of the dependent arithmetic.
-        const bool all_fast = __ballot_sync(kFullMask, grp[lane] != 0) == 0;   // no freq <= 16 / generic symbol in the block
         if (lane0) {
             uint4 ea[16];
-            uint2 es[16];
+            uint32_t es[16];
 #pragma unroll
             for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + 31]; es[b] = st_s[b * 32 + 31]; }
-            // one group of 16 symbols whose freqs are all in (16, 4096]: at most one renormalisation byte per symbol.
-            // Both outcomes are computed and selected at the end, so the comparison is off the critical path.
-            auto fast_group = [&](int c, int cn) {
+            uint32_t g = grp[31];
+            for (int c = 31; c >= 0; c--) {
+                const int cn = c > 0 ? c - 1 : 0;
+                const uint32_t gn = grp[cn];
+                if (g == 0) {
+                    // every freq in (16, 4096]: at most one renormalisation byte per symbol.  Both outcomes are
+                    // computed and selected at the end, so the comparison is off the critical path.
 #pragma unroll
-                for (int b = 15; b >= 0; b--) {
-                    st_x[b * 32 + c] = x;
-                    const bool k = x > ea[b].x;
-                    const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
-                    const uint32_t xa = (hi >> es[b].x) * ea[b].z + (x + ea[b].w);
-                    // floor(floor(x/f) / 256) == floor((x >> 8) / f)
-                    const uint32_t xb = (hi >> es[b].y) * ea[b].z + ((x >> 8) + ea[b].w);
-                    x = k ? xb : xa;
-                    ea[b] = st_a[b * 32 + cn];
-                    es[b] = st_s[b * 32 + cn];
-                }
-            };
-            if (all_fast) {
-                for (int c = 31; c >= 0; c--) fast_group(c, (c + 31) & 31);   // the last prefetch (group 31 again) is unused
-            } else {
-                uint32_t g = grp[31];
-                for (int c = 31; c >= 0; c--) {
-                    const int cn = (c + 31) & 31;
-                    const uint32_t gn = grp[cn];
-                    if (g == 0) {
-                        fast_group(c, cn);
-                    } else if (!(g & kGrpGeneric)) {
-                        // some freq in [2, 16]: up to two renormalisation bytes
-#pragma unroll
-                        for (int b = 15; b >= 0; b--) {
-                            st_x[b * 32 + c] = x;
-                            const uint32_t lim = ea[b].x;
-                            const uint32_t lim2 = (es[b].x & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
-                            const uint32_t sh = es[b].x & 0xffu;
-                            const bool k1 = x > lim, k2 = x > lim2;
-                            const uint32_t hi = __umulhi(x, ea[b].y);
-                            uint32_t sx = k1 ? 8u : 0u;
-                            sx = k2 ? 16u : sx;
-                            x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
-                            ea[b] = st_a[b * 32 + cn];
-                            es[b] = st_s[b * 32 + cn];
-                        }
-                    } else {
-                        for (int b = 15; b >= 0; b--) {
-                            const uint4 e = tab[st_sym[b * 32 + c]];
-                            st_x[b * 32 + c] = x;
-                            if (e.w & kEncZero) { status |= 2u; continue; }
-                            while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
-                            const uint32_t f = kProbScale - e.z;
-                            const uint32_t q = x / f;
-                            x = x + (e.w & 0xffffu) + q * e.z;
-                        }
-#pragma unroll
-                        for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
+                    for (int b = 15; b >= 0; b--) {
+                        st_x[b * 32 + c] = x;
+                        const bool k = x > ea[b].x;
+                        const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
+                        const uint32_t sh = es[b];
+                        const uint32_t xa = (hi >> sh) * ea[b].z + (x + ea[b].w);
+                        // floor(floor(x/f) / 256) == floor((x >> 8) / f)
+                        const uint32_t xb = (hi >> (sh + 8u)) * ea[b].z + ((x >> 8) + ea[b].w);
+                        x = k ? xb : xa;
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
                     }
-                    g = gn;
+                } else if (!(g & kGrpGeneric)) {
+                    // some freq in [2, 16]: up to two renormalisation bytes
+#pragma unroll
+                    for (int b = 15; b >= 0; b--) {
+                        st_x[b * 32 + c] = x;
+                        const uint32_t lim = ea[b].x;
+                        const uint32_t lim2 = (es[b] & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
+                        const uint32_t sh = es[b] & 0xffu;
+                        const bool k1 = x > lim, k2 = x > lim2;
+                        const uint32_t hi = __umulhi(x, ea[b].y);
+                        uint32_t sx = k1 ? 8u : 0u;
+                        sx = k2 ? 16u : sx;
+                        x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
+                    }
+                } else {
+                    for (int b = 15; b >= 0; b--) {
+                        const uint4 e = tab[st_sym[b * 32 + c]];
+                        st_x[b * 32 + c] = x;
+                        if (e.w & kEncZero) { status |= 2u; continue; }
+                        while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
+                        const uint32_t f = kProbScale - e.z;
+                        const uint32_t q = x / f;
+                        x = x + (e.w & 0xffffu) + q * e.z;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
                 }
+                g = gn;
             }
         }
         __syncwarp();

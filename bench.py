@@ -158,11 +158,15 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--e2e-only", action="store_true", help="skip the device-resident timed region (debug)")
     ap.add_argument("--quality", type=int, default=QUALITY)
     ap.add_argument("--wavelet", default=WAVELET)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: at least 3 warm-up steps
+    if args.e2e_only:                        # debugging aid: the printed `value` is then not a valid measurement
+        args.warmup, args.steps = 0, 1
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -327,9 +331,14 @@ def main():
             for it in range(1 + args.e2e_steps):        # iteration 0 = warm-up (staging buffers, first-touch)
                 if it < 2:
                     gate.wait()                         # start of the warm-up / of the timed region
+                ta = time.perf_counter()
                 chunks = batches[t].encode_host(hin)    # H2D RGB, kernels, D2H headers + payload
+                tb = time.perf_counter()
                 payload[t] = sum(c.compressed_size + 3138 for c in chunks)
                 batches[t].decode_host(chunks, hout)    # H2D payload, kernels, D2H RGB
+                tc = time.perf_counter()
+                if args.verbose:
+                    sys.stderr.write(f"[e2e] thread {t} it {it}: encode_host {tb - ta:.2f} s, decode_host {tc - tb:.2f} s\n")
                 if it == 0 or it == args.e2e_steps:
                     gate.wait()                         # end of the warm-up / of the timed region
         threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]

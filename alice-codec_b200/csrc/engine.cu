@@ -160,6 +160,7 @@ Engine::~Engine() {
     cudaFree(d_aux_); cudaFree(d_payload_); cudaFree(d_enc_jobs_); cudaFree(d_dec_jobs_); cudaFree(d_results_);
     for (uint8_t *p : rgb_stage_) cudaFree(p);
     for (uint8_t *p : overflow_bufs_) if (p) cudaFree(p);
+    if (h_pay_) cudaFreeHost(h_pay_);
     if (h_results_) cudaFreeHost(h_results_);
     if (h_hist_) cudaFreeHost(h_hist_);
     if (h_enc_jobs_) cudaFreeHost(h_enc_jobs_);
@@ -167,6 +168,19 @@ Engine::~Engine() {
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     if (st_ && own_stream_) cudaStreamDestroy(st_);
     cudaGetLastError();
+}
+
+bool Engine::ensure_pinned_payload(size_t bytes) {
+    if (bytes <= h_pay_cap_) return true;
+    if (h_pay_) { cudaFreeHost(h_pay_); h_pay_ = nullptr; h_pay_cap_ = 0; }
+    const size_t want = round_up(bytes + bytes / 4 + 4096, 4096);
+    if (cudaMallocHost((void **)&h_pay_, want) != cudaSuccess) {
+        cudaGetLastError();
+        set_error(kErrCuda, "pinned host allocation failed (payload staging)");
+        return false;
+    }
+    h_pay_cap_ = want;
+    return true;
 }
 
 uint8_t *Engine::rgb_stage(uint32_t slot) {
@@ -269,16 +283,18 @@ int Engine::fetch_chunk(uint32_t i, Chunk &out) {
         memcpy(h.histogram, h_hist_ + (size_t)s * 256, 256 * sizeof(uint32_t));
         total += stream_len_[s];
     }
-    out.data.resize(total);
+    // payload: device -> pinned staging (DMA at link speed, no driver bounce buffer) -> the chunk's vector
+    if (!ensure_pinned_payload(total)) return kErrCuda;
     size_t off = 0;
     for (int c = 0; c < 3; c++) {
         const uint32_t s = i * 3 + c;
         if (stream_len_[s])
-            CU_TRY(cudaMemcpyAsync(out.data.data() + off, stream_base_[s] + stream_off_[s], stream_len_[s],
+            CU_TRY(cudaMemcpyAsync(h_pay_ + off, stream_base_[s] + stream_off_[s], stream_len_[s],
                                    cudaMemcpyDeviceToHost, st_));
         off += stream_len_[s];
     }
     CU_TRY(cudaStreamSynchronize(st_));
+    out.data.assign(h_pay_, h_pay_ + total);
     return kOk;
 }
 
@@ -338,6 +354,8 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
     for (uint32_t i = 0; i < n; i++) {
         const Chunk &ck = *chunks[i];
         size_t off = 0;
+        CU_TRY(cudaStreamSynchronize(st_));   // the previous chunk's copies out of the staging buffer have landed
+        if (!ensure_pinned_payload(ck.data.size())) return kErrCuda;
         for (int c = 0; c < 3; c++) {
             const uint32_t s = i * 3 + c;
             memcpy(h_hist_ + (size_t)s * 256, ck.ch[c].histogram, 256 * sizeof(uint32_t));
@@ -352,7 +370,11 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
                 }
                 dst = overflow_bufs_[s];
             }
-            if (len) CU_TRY(cudaMemcpyAsync(dst, ck.data.data() + off, len, cudaMemcpyHostToDevice, st_));
+            if (len) {
+                // host vector -> pinned staging -> device; the staging buffer is reused once the copy has landed
+                memcpy(h_pay_ + off, ck.data.data() + off, len);
+                CU_TRY(cudaMemcpyAsync(dst, h_pay_ + off, len, cudaMemcpyHostToDevice, st_));
+            }
             off += len;
             h_dec_jobs_[s].in = dst;
             h_dec_jobs_[s].len = len;

@@ -105,6 +105,9 @@ private:
     unsigned long long *d_results_ = nullptr;  // [cap*3][2]
     std::vector<uint8_t *> rgb_stage_;
     std::vector<uint8_t *> overflow_bufs_;     // per stream, full-size retry buffers (rare)
+    uint8_t *h_pay_ = nullptr;                 // pinned staging for one chunk's payload (host <-> device)
+    size_t h_pay_cap_ = 0;
+    bool ensure_pinned_payload(size_t bytes);
     // pinned host mirrors
     unsigned long long *h_results_ = nullptr;
     unsigned *h_hist_ = nullptr;

@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -38,6 +39,85 @@ bool cuda_ready() {
     return true;
 }
 
+// ------------------------------------------------------------------------------ ByteBuf
+namespace {
+struct PoolEntry2 { uint8_t *p; size_t cap; };
+std::mutex g_buf_mu;
+std::vector<PoolEntry2> g_buf_pool;
+size_t g_buf_pool_bytes = 0;
+size_t buf_pool_limit() {
+    static size_t lim = [] {
+        const char *e = getenv("ALICE_CODEC_PINNED_POOL_MB");
+        long long mb = e ? atoll(e) : 16384;
+        return (size_t)(mb < 0 ? 0 : mb) << 20;
+    }();
+    return lim;
+}
+}  // namespace
+
+bool ByteBuf::assign(const uint8_t *src, size_t n) {
+    release();
+    p_ = (uint8_t *)malloc(n ? n : 1);
+    if (!p_) return false;
+    if (n) memcpy(p_, src, n);
+    n_ = cap_ = n;
+    pinned_ = false;
+    return true;
+}
+
+bool ByteBuf::acquire_pinned(size_t n) {
+    release();
+    {
+        std::lock_guard<std::mutex> lk(g_buf_mu);
+        size_t best = g_buf_pool.size();
+        for (size_t i = 0; i < g_buf_pool.size(); i++)
+            if (g_buf_pool[i].cap >= n && (best == g_buf_pool.size() || g_buf_pool[i].cap < g_buf_pool[best].cap)) best = i;
+        if (best != g_buf_pool.size()) {
+            p_ = g_buf_pool[best].p;
+            cap_ = g_buf_pool[best].cap;
+            g_buf_pool_bytes -= cap_;
+            g_buf_pool.erase(g_buf_pool.begin() + (long)best);
+            n_ = n;
+            pinned_ = true;
+            return true;
+        }
+    }
+    const size_t cap = (n + n / 8 + 4095) / 4096 * 4096 + 4096;   // head-room so similar chunks share buffers
+    void *q = nullptr;
+    if (posix_memalign(&q, 4096, cap) != 0) return false;
+    if (cudaHostRegister(q, cap, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        free(q);
+        return false;
+    }
+    p_ = (uint8_t *)q;
+    cap_ = cap;
+    n_ = n;
+    pinned_ = true;
+    return true;
+}
+
+void ByteBuf::release() {
+    if (!p_) return;
+    if (pinned_) {
+        std::unique_lock<std::mutex> lk(g_buf_mu);
+        if (g_buf_pool_bytes + cap_ <= buf_pool_limit()) {
+            g_buf_pool.push_back({p_, cap_});
+            g_buf_pool_bytes += cap_;
+        } else {
+            lk.unlock();
+            cudaHostUnregister(p_);
+            cudaGetLastError();
+            free(p_);
+        }
+    } else {
+        free(p_);
+    }
+    p_ = nullptr;
+    n_ = cap_ = 0;
+    pinned_ = false;
+}
+
 // ------------------------------------------------------------------------- .alc container
 static void put_u32(std::vector<uint8_t> &b, uint32_t v) {
     b.push_back((uint8_t)v); b.push_back((uint8_t)(v >> 8)); b.push_back((uint8_t)(v >> 16)); b.push_back((uint8_t)(v >> 24));
@@ -62,7 +142,7 @@ std::vector<uint8_t> Chunk::to_bytes() const {
         put_u32(buf, c.num_symbols);
         for (uint32_t v : c.histogram) put_u32(buf, v);
     }
-    buf.insert(buf.end(), data.begin(), data.end());
+    buf.insert(buf.end(), data.data(), data.data() + data.size());
     return buf;
 }
 
@@ -87,7 +167,7 @@ int Chunk::from_bytes(const uint8_t *p, size_t len, Chunk &out) {
         total += c.compressed_len;
     }
     if (len < off + total) { set_error(kErrBitstream, "truncated payload"); return kErrBitstream; }
-    out.data.assign(p + off, p + off + total);  // trailing bytes are ignored, pipeline.rs:303
+    if (!out.data.assign(p + off, total)) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }  // trailing bytes are ignored, pipeline.rs:303
     return kOk;
 }
 
@@ -283,18 +363,24 @@ int Engine::fetch_chunk(uint32_t i, Chunk &out) {
         memcpy(h.histogram, h_hist_ + (size_t)s * 256, 256 * sizeof(uint32_t));
         total += stream_len_[s];
     }
-    // payload: device -> pinned staging (DMA at link speed, no driver bounce buffer) -> the chunk's vector
-    if (!ensure_pinned_payload(total)) return kErrCuda;
+    // payload: the device writes straight into the chunk's page-locked buffer (pooled, see ByteBuf)
+    uint8_t *dst = nullptr;
+    const bool direct = out.data.acquire_pinned(total);
+    if (direct) dst = out.data.data();
+    else {
+        if (!ensure_pinned_payload(total)) return kErrCuda;
+        dst = h_pay_;
+    }
     size_t off = 0;
     for (int c = 0; c < 3; c++) {
         const uint32_t s = i * 3 + c;
         if (stream_len_[s])
-            CU_TRY(cudaMemcpyAsync(h_pay_ + off, stream_base_[s] + stream_off_[s], stream_len_[s],
+            CU_TRY(cudaMemcpyAsync(dst + off, stream_base_[s] + stream_off_[s], stream_len_[s],
                                    cudaMemcpyDeviceToHost, st_));
         off += stream_len_[s];
     }
     CU_TRY(cudaStreamSynchronize(st_));
-    out.data.assign(h_pay_, h_pay_ + total);
+    if (!direct && !out.data.assign(h_pay_, total)) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
     return kOk;
 }
 
@@ -354,8 +440,11 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
     for (uint32_t i = 0; i < n; i++) {
         const Chunk &ck = *chunks[i];
         size_t off = 0;
-        CU_TRY(cudaStreamSynchronize(st_));   // the previous chunk's copies out of the staging buffer have landed
-        if (!ensure_pinned_payload(ck.data.size())) return kErrCuda;
+        const bool direct = ck.data.pinned();     // page-locked buffer: the device reads it directly
+        if (!direct) {
+            CU_TRY(cudaStreamSynchronize(st_));   // the previous chunk's copies out of the staging buffer have landed
+            if (!ensure_pinned_payload(ck.data.size())) return kErrCuda;
+        }
         for (int c = 0; c < 3; c++) {
             const uint32_t s = i * 3 + c;
             memcpy(h_hist_ + (size_t)s * 256, ck.ch[c].histogram, 256 * sizeof(uint32_t));
@@ -372,8 +461,9 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             }
             if (len) {
                 // host vector -> pinned staging -> device; the staging buffer is reused once the copy has landed
-                memcpy(h_pay_ + off, ck.data.data() + off, len);
-                CU_TRY(cudaMemcpyAsync(dst, h_pay_ + off, len, cudaMemcpyHostToDevice, st_));
+                const uint8_t *src = ck.data.data() + off;
+                if (!direct) { memcpy(h_pay_ + off, src, len); src = h_pay_ + off; }
+                CU_TRY(cudaMemcpyAsync(dst, src, len, cudaMemcpyHostToDevice, st_));
             }
             off += len;
             h_dec_jobs_[s].in = dst;

@@ -32,11 +32,37 @@ struct ChannelHeader {              // pipeline.rs:123-134
 constexpr size_t kChannelHeaderBytes = 1040;  // pipeline.rs:137
 constexpr size_t kFixedHeaderBytes = 18;      // pipeline.rs:148
 
+// Payload bytes of a chunk.  Buffers filled by the encoder come from a process-wide pool of page-locked
+// (cudaHostRegister) allocations, so the device writes them directly at link speed and a destroyed chunk's buffer is
+// reused by the next encode instead of being unmapped and page-faulted in again (ALICE_CODEC_PINNED_POOL_MB bounds
+// the idle pool, default 16384).  Buffers filled from user bytes (from_bytes) are plain malloc.
+class ByteBuf {
+public:
+    ByteBuf() = default;
+    ~ByteBuf() { release(); }
+    ByteBuf(const ByteBuf &) = delete;
+    ByteBuf &operator=(const ByteBuf &) = delete;
+    ByteBuf(ByteBuf &&o) noexcept { steal(o); }
+    ByteBuf &operator=(ByteBuf &&o) noexcept { if (this != &o) { release(); steal(o); } return *this; }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+    bool pinned() const { return pinned_; }
+    bool assign(const uint8_t *src, size_t n);   // plain heap copy
+    bool acquire_pinned(size_t n);               // page-locked storage of n bytes (contents undefined)
+    void release();
+private:
+    void steal(ByteBuf &o) { p_ = o.p_; n_ = o.n_; cap_ = o.cap_; pinned_ = o.pinned_; o.p_ = nullptr; o.n_ = o.cap_ = 0; o.pinned_ = false; }
+    uint8_t *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+    bool pinned_ = false;
+};
+
 struct Chunk {                      // pipeline.rs:172-185
     uint32_t width = 0, height = 0, frames = 0;
     uint8_t wavelet = 0;
     ChannelHeader ch[3];
-    std::vector<uint8_t> data;      // concatenated rANS streams Y | Co | Cg
+    ByteBuf data;                   // concatenated rANS streams Y | Co | Cg
     std::vector<uint8_t> to_bytes() const;                                   // pipeline.rs:200-226
     static int from_bytes(const uint8_t *data, size_t len, Chunk &out);      // pipeline.rs:235-313
 };

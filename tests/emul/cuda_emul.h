@@ -274,6 +274,9 @@ inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc((void **)p, n); }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+enum { cudaHostRegisterDefault = 0, cudaHostRegisterPortable = 1 };
+inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }

@@ -30,3 +30,13 @@ for it in range(2):
     ms = b.timings()
     print(f"it {it}: encode_host {t1 - t0:.3f} s (kernels {sum(ms[:3]) / 1e3:.3f}), decode_host {t2 - t1:.3f} s (kernels {sum(ms[3:6]) / 1e3:.3f}); "
           f"rgb bytes {a.chunks * n / 1e9:.2f} GB each way, payload {sum(c.compressed_size for c in ck) / 1e9:.2f} GB")
+# component timing through the device-pointer API
+d_ins = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(a.chunks)]
+for it in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for i in range(a.chunks): d_ins[i].copy_(h_in[i], non_blocking=True)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    b.encode_device([t.data_ptr() for t in d_ins]); t2 = time.perf_counter()
+    cks = [b.get_chunk(i) for i in range(a.chunks)]; t3 = time.perf_counter()
+    del cks; t4 = time.perf_counter()
+    print(f"components it {it}: H2D {t1 - t0:.3f} s, encode_device {t2 - t1:.3f} s (kernels {sum(b.timings()[:3]) / 1e3:.3f}), get_chunk x{a.chunks} {t3 - t2:.3f} s, destroy {t4 - t3:.3f} s")

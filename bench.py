@@ -308,6 +308,12 @@ def main():
         # The caller-side pattern for host buffers: T host threads, each driving its own ChunkBatch (own CUDA stream)
         # over its share of the chunks, so one batch's PCIe copies run under another batch's rANS kernels.
         Be = args.e2e_chunks or B
+        try:                                            # pinned RGB in + out must fit the host comfortably (all ranks)
+            import psutil
+            host_avail = psutil.virtual_memory().available
+            Be = max(1, min(Be, int(host_avail * 0.5 / world // (2 * rgb_bytes))))
+        except Exception:  # noqa: BLE001
+            Be = min(Be, 32)
         T = max(1, min(args.e2e_threads, Be))
         h_in = [torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory() for _ in range(Be)]
         h_out = [torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory() for _ in range(Be)]

@@ -158,11 +158,9 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
         if (has && j - NST >= i0 && j - NST < i1) emit(j - NST, lo, hi);
         cur[0] = nxt[0]; cur[1] = nxt[1];
     }
-    // steady state: two row pairs are in flight while this one is transformed (cur <- nxt <- nn)
-    RowRaw<M> nn[2];
-    if (j < je) load_pair(min(j + 1, je - 1), nxt);
+    // steady state: the next row pair is already in flight while this one is transformed
     for (; j < je; j++, k++) {
-        load_pair(min(j + 2, je - 1), nn);
+        load_pair(min(j + 1, je - 1), nxt);
         int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];
         row_x(cur[0], v0);
         row_x(cur[1], v1);
@@ -172,7 +170,6 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
             for (int i = 0; i < PXL; i++) L[c][i].push_steady(v0[c][i], v1[c][i], lo[c][i], hi[c][i]);
         emit(j - NST, lo, hi);
         cur[0] = nxt[0]; cur[1] = nxt[1];
-        nxt[0] = nn[0]; nxt[1] = nn[1];
     }
     if (je == halfy && k > 0) {
 #pragma unroll

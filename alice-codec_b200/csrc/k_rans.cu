@@ -239,9 +239,6 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         ((fl & ((kEncWide | kEncZero | kEncOne) >> 24)) ? kGrpGeneric : 0u);
         }
         __syncwarp();
-        // group kinds as two warp-wide bit masks (bit c = group c), so the serial loop tests a register bit
-        const uint32_t m_notfast = __ballot_sync(kFullMask, grp[lane] != 0);
-        const uint32_t m_generic = __ballot_sync(kFullMask, (grp[lane] & kGrpGeneric) != 0);
         // ---- lane 0 only: the state recurrence, last symbol first.  It records the state before each step in
         // st_x; which bytes that step emitted is recomputed from (state, limit) by all lanes afterwards, so the
         // serial code has no stream pointer to maintain.  (One active lane also makes every 16-byte shared load a
@@ -252,9 +249,11 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
             uint32_t es[16];
 #pragma unroll
             for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + 31]; es[b] = st_s[b * 32 + 31]; }
+            uint32_t g = grp[31];
             for (int c = 31; c >= 0; c--) {
-                const int cn = (c + 31) & 31;            // next group; after group 0 the prefetch (group 31 again) is unused
-                if (!((m_notfast >> c) & 1u)) {
+                const int cn = c > 0 ? c - 1 : 0;
+                const uint32_t gn = grp[cn];
+                if (g == 0) {
                     // every freq in (16, 4096]: at most one renormalisation byte per symbol.  Both outcomes are
                     // computed and selected at the end, so the comparison is off the critical path.
 #pragma unroll
@@ -270,7 +269,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         ea[b] = st_a[b * 32 + cn];
                         es[b] = st_s[b * 32 + cn];
                     }
-                } else if (!((m_generic >> c) & 1u)) {
+                } else if (!(g & kGrpGeneric)) {
                     // some freq in [2, 16]: up to two renormalisation bytes
 #pragma unroll
                     for (int b = 15; b >= 0; b--) {
@@ -299,6 +298,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
 #pragma unroll
                     for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
                 }
+                g = gn;
             }
         }
         __syncwarp();

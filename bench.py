@@ -152,8 +152,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=0, help="chunks in flight per GPU (0 = sized from free HBM)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (0 = same as --chunks)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=3)
+    ap.add_argument("--e2e-stagger", type=float, default=2.5, help="seconds between the first starts of the e2e host threads")
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--cpu-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -340,15 +341,18 @@ def main():
         batches = [pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, len(shares[t]), stream=streams[t].cuda_stream,
                                   api=api) for t in range(T)]
         payload = [0] * T
-        gate = threading.Barrier(T + 1)
+        t_start, t_end = [0.0] * T, [0.0] * T
+        go = threading.Barrier(T + 1)
 
         def worker(t):
             api.set_device(local)                       # cudaSetDevice is per host thread
             hin = [h_in[i].data_ptr() for i in shares[t]]
             hout = [h_out[i].data_ptr() for i in shares[t]]
-            for it in range(1 + args.e2e_steps):        # iteration 0 = warm-up (staging buffers, first-touch)
-                if it < 2:
-                    gate.wait()                         # start of the warm-up / of the timed region
+            go.wait()
+            time.sleep(t * args.e2e_stagger)            # start the batches out of phase: copies of one run under
+            for it in range(1 + args.e2e_steps):        # the rANS kernels of the others.  Iteration 0 = warm-up.
+                if it == 1:
+                    t_start[t] = time.perf_counter()
                 ta = time.perf_counter()
                 chunks = batches[t].encode_host(hin)    # H2D RGB, kernels, D2H headers + payload
                 tb = time.perf_counter()
@@ -357,19 +361,18 @@ def main():
                 tc = time.perf_counter()
                 if args.verbose:
                     sys.stderr.write(f"[e2e] thread {t} it {it}: encode_host {tb - ta:.2f} s, decode_host {tc - tb:.2f} s\n")
-                if it == 0 or it == args.e2e_steps:
-                    gate.wait()                         # end of the warm-up / of the timed region
+            t_end[t] = time.perf_counter()
         threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
         for th in threads:
             th.start()
-        gate.wait(); gate.wait()                        # warm-up iteration
         barrier()
-        t0 = time.perf_counter()
-        gate.wait(); gate.wait()                        # the threads run their e2e_steps back to back, unsynchronised
-        barrier()
-        dt = time.perf_counter() - t0
+        go.wait()
         for th in threads:
             th.join()
+        barrier()
+        # the timed window runs from the first thread's first timed iteration to the last thread's last one; parts
+        # of other threads' warm-up iterations that fall inside it are not counted as work
+        dt = max(t_end) - min(t_start)
         if world > 1:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

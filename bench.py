@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (0 = same as --chunks)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=3)
-    ap.add_argument("--e2e-stagger", type=float, default=2.5, help="seconds between the first starts of the e2e host threads")
+    ap.add_argument("--e2e-stagger", type=float, default=0.0, help="seconds between the first starts of the e2e host threads")
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--cpu-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")

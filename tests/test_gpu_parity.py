@@ -111,6 +111,33 @@ def test_fullsize_odd_and_noise(api):
     _fullsize(api, "noise_cdf53_q90_1080p8", want_coeffs=True)
 
 
+def test_fullsize_config5_two_4k_chunks_through_the_batch_api(api):
+    """BASELINE config 5 (3840x2160x512 = 8 chunks of 64 frames, CDF 9/7 q=80, chunk c = G1 seed + c): two of the
+    chunks in flight through the batch API, .alc and decoded RGB against the oracle digests."""
+    import ctypes as C
+    import torch
+    g = json.load(open(GOLDEN_PATH))
+    names = ["cfg5_cdf97_q80_4k64_chunk0", "cfg5_cdf97_q80_4k64_chunk1"]
+    w, h, f = 3840, 2160, 64
+    st = torch.cuda.current_stream()
+    d_in = [torch.empty(w * h * f * 3, dtype=torch.uint8, device="cuda") for _ in names]
+    for t, nm in zip(d_in, names):
+        api._chk(api.lib.alice_codec_synth_rgb_device(g[nm]["kind"], g[nm]["seed"], w, h, f, C.c_void_p(t.data_ptr()),
+                                                      C.c_void_p(st.cuda_stream)))
+    batch = pkg.ChunkBatch(80, "cdf97", w, h, f, len(names), stream=st.cuda_stream, api=api)
+    batch.encode_device([t.data_ptr() for t in d_in])
+    for i, nm in enumerate(names):
+        assert sha(d_in[i].cpu().numpy().tobytes()) == g[nm]["sha256_rgb_in"]
+        alc = batch.get_chunk(i).to_bytes()
+        assert len(alc) == g[nm]["alc_len"]
+        assert sha(alc) == g[nm]["sha256_alc"], f"{nm}: .alc differs from the oracle digest"
+    batch.decode_device([t.data_ptr() for t in d_in])        # in place: decode does not read the RGB input
+    torch.cuda.synchronize()
+    for i, nm in enumerate(names):
+        assert sha(d_in[i].cpu().numpy().tobytes()) == g[nm]["sha256_decoded"], f"{nm}: decoded RGB differs"
+    batch.close()
+
+
 def test_stage_apis(api):
     rng = np.random.default_rng(1)
     parity.check_wavelet_api(api, rng, [2, 3, 8, 9, 31, 1000, 1921], [(4, 4), (5, 3), (16, 9), (321, 65)],

@@ -28,37 +28,48 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
     return (int)((unsigned)q * (unsigned)step);
 }
 
-template <int WT, int VEC, int PF>
-__global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 2 : 4))
-k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw, int ph, int f, int pf, int step0,
+// WIDE = true : the reference's wrapping i32 arithmetic with the i64 lifting product, i32 hand-off (any header).
+// WIDE = false: 32-bit products and an i16 hand-off, exact while 128 * |quant_step| <= kNarrowMaxCoef (see launcher).
+template <bool WIDE> struct Handoff { typedef int32_t T; };
+template <> struct Handoff<false> { typedef int16_t T; };
+
+template <int WT, int VEC, int PF, bool WIDE>
+__global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 3 : 4))
+k_inv_t(const uint8_t *__restrict__ symbols, void *__restrict__ coef_v, int pw, int ph, int f, int pf, int step0,
         int step1, int step2) {
+    typedef typename Handoff<WIDE>::T HT;
+    HT *coef = reinterpret_cast<HT *>(coef_v);
     constexpr int NST = WaveletTraits<WT>::NST;
     const int c = blockIdx.z;
     const int step = c == 0 ? step0 : (c == 1 ? step1 : step2);
     const int halft = PF ? PF / 2 : (pf >> 1);   // PF != 0: compile-time depth, the streaming state machine unrolls away
     const size_t frame_sz = (size_t)ph * pw;
     const uint8_t *src = symbols + (size_t)c * pf * frame_sz;
-    int32_t *dst = coef + (size_t)c * f * frame_sz;
+    HT *dst = coef + (size_t)c * f * frame_sz;
     const long long n_items = (long long)(frame_sz / VEC);
 
+    auto store_vec = [&](HT *p, const int (&v)[VEC]) {
+        if (WIDE) {
+            if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(v[0], v[1], v[VEC - 2], v[VEC - 1]);
+            else *reinterpret_cast<int2 *>(p) = make_int2(v[0], v[1]);
+        } else {
+            const uint32_t w0 = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+            if (VEC == 4) {
+                const uint32_t w1 = (uint32_t)(uint16_t)v[VEC - 2] | ((uint32_t)(uint16_t)v[VEC - 1] << 16);
+                *reinterpret_cast<uint2 *>(p) = make_uint2(w0, w1);
+            } else *reinterpret_cast<uint32_t *>(p) = w0;
+        }
+    };
     auto emit = [&](size_t off, int jo, const int (&ev)[VEC], const int (&od)[VEC]) {
         const int t0 = 2 * jo, t1 = 2 * jo + 1;
-        if (t0 < f) {
-            int32_t *p = dst + (size_t)t0 * frame_sz + off;
-            if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(ev[0], ev[1], ev[VEC - 2], ev[VEC - 1]);
-            else *reinterpret_cast<int2 *>(p) = make_int2(ev[0], ev[1]);
-        }
-        if (t1 < f) {
-            int32_t *p = dst + (size_t)t1 * frame_sz + off;
-            if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(od[0], od[1], od[VEC - 2], od[VEC - 1]);
-            else *reinterpret_cast<int2 *>(p) = make_int2(od[0], od[1]);
-        }
+        if (t0 < f) store_vec(dst + (size_t)t0 * frame_sz + off, ev);
+        if (t1 < f) store_vec(dst + (size_t)t1 * frame_sz + off, od);
     };
 
     for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
          item += (long long)gridDim.x * blockDim.x) {
         const size_t off = (size_t)item * VEC;
-        InvLift<WT, true> L[VEC];
+        InvLift<WT, WIDE> L[VEC];
         int k = 0;
 #pragma unroll
         for (int j = 0; j < halft; j++, k++) {
@@ -91,12 +102,18 @@ k_inv_t(const uint8_t *__restrict__ symbols, int32_t *__restrict__ coef, int pw,
     }
 }
 
-template <int M>
-ALICE_D void load_group_i32(const int32_t *__restrict__ row, int xp, int limit, int *v) {
-    if (xp >= 0 && M == 2 && xp + 2 <= limit && ((reinterpret_cast<uintptr_t>(row + xp) & 7) == 0)) {
-        int2 t = __ldg(reinterpret_cast<const int2 *>(row + xp));
-        v[0] = t.x;
-        v[1] = t.y;
+template <int M, class HT>
+ALICE_D void load_group_i32(const HT *__restrict__ row, int xp, int limit, int *v) {
+    if (xp >= 0 && M == 2 && xp + 2 <= limit && ((reinterpret_cast<uintptr_t>(row + xp) & (2 * sizeof(HT) - 1)) == 0)) {
+        if (sizeof(HT) == 4) {
+            int2 t = __ldg(reinterpret_cast<const int2 *>(row + xp));
+            v[0] = t.x;
+            v[1] = t.y;
+        } else {
+            const uint32_t t = __ldg(reinterpret_cast<const uint32_t *>(row + xp));
+            v[0] = (int16_t)(t & 0xffff);
+            v[1] = (int)t >> 16;
+        }
         return;
     }
 #pragma unroll
@@ -108,9 +125,9 @@ ALICE_D void load_group_i32(const int32_t *__restrict__ row, int xp, int limit, 
 
 ALICE_D uint32_t clamp_u8(int16_t v) { return v < 0 ? 0u : (v > 255 ? 255u : (uint32_t)v); }
 
-template <int WT, int M>
+template <int WT, int M, bool WIDE>
 __global__ void ALICE_LAUNCH_BOUNDS(128, 3)
-k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int h, int f, int pw, int ph,
+k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int h, int f, int pw, int ph,
          int n_strips, int n_segs, int seg_pairs, int vec_ok) {
     constexpr int NST = WaveletTraits<WT>::NST;
     constexpr int PXL = 2 * M;
@@ -131,9 +148,11 @@ k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int
     const int js = max(0, i0 - NST);
     const int je = min(halfy, i1 + NST);
 
-    InvLift<WT, true> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
+    typedef typename Handoff<WIDE>::T HT;
+    const HT *coef = reinterpret_cast<const HT *>(coef_v);
+    InvLift<WT, WIDE> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
     const size_t plane_sz = (size_t)f * ph * pw;
-    const int32_t *in_t = coef + (size_t)t * ph * pw;
+    const HT *in_t = coef + (size_t)t * ph * pw;
     uint8_t *frame = rgb + (size_t)t * w * h * 3;
 
     // one reconstructed image row y from its x-subband values (all lanes take part in the shuffles)
@@ -144,7 +163,7 @@ k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int
             int e[M], o[M];
 #pragma unroll
             for (int i = 0; i < M; i++) { e[i] = val[c][i]; o[i] = val[c][M + i]; }
-            inv_lanes<WT, true, M>(e, o, p0, halfx);
+            inv_lanes<WT, WIDE, M>(e, o, p0, halfx);
 #pragma unroll
             for (int i = 0; i < M; i++) { px[c][2 * i] = e[i]; px[c][2 * i + 1] = o[i]; }
         }
@@ -186,13 +205,13 @@ k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int
         bool has = false;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const int32_t *row_lo = in_t + c * plane_sz + (size_t)j * pw;
-            const int32_t *row_hi = in_t + c * plane_sz + (size_t)(halfy + j) * pw;
+            const HT *row_lo = in_t + c * plane_sz + (size_t)j * pw;
+            const HT *row_hi = in_t + c * plane_sz + (size_t)(halfy + j) * pw;
             int lo[PXL], hi[PXL];
-            load_group_i32<M>(row_lo, p0, halfx, &lo[0]);
-            load_group_i32<M>(row_lo + halfx, p0, halfx, &lo[M]);
-            load_group_i32<M>(row_hi, p0, halfx, &hi[0]);
-            load_group_i32<M>(row_hi + halfx, p0, halfx, &hi[M]);
+            load_group_i32<M, HT>(row_lo, p0, halfx, &lo[0]);
+            load_group_i32<M, HT>(row_lo + halfx, p0, halfx, &lo[M]);
+            load_group_i32<M, HT>(row_hi, p0, halfx, &hi[0]);
+            load_group_i32<M, HT>(row_hi + halfx, p0, halfx, &hi[M]);
 #pragma unroll
             for (int i = 0; i < PXL; i++) has = L[c][i].push(lo[i], hi[i], k, j, ev[c][i], od[c][i]);
         }
@@ -222,7 +241,15 @@ k_inv_yx(const int32_t *__restrict__ coef, uint8_t *__restrict__ rgb, int w, int
     }
 }
 
-template <int WT>
+// Largest |coefficient| = 128 * |quant_step| (|q| <= 128 for u8 symbols) for which the narrow variant is exact.
+// Worst-case gains of the linear part of the inverse lifting (max abs row sums over every intermediate stage,
+// n = 64; rounding adds < 1 per step): values 2.2744 / 2.0 / 2.0 per axis and 1.6663 / 2.0 / 2.0 at the end of an
+// axis, neighbour sums (a+b) 4.549 / 2.5 / 3.0 (CDF 9/7 / CDF 5/3 / Haar).  With A = 15000: the i16 hand-off after
+// the t pass holds <= 2.0 A = 30000; the largest product in the x pass is 4.549 * 1.6663^2 A * 6497 = 1.2e9
+// (9/7), 3.0 * 4 A * 4096 = 7.4e8 (Haar) < 2^31.
+constexpr long long kNarrowMaxCoef = 15000;
+
+template <int WT, bool WIDE>
 static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f, int pw, int ph,
                        int pf, const int steps[3], cudaStream_t st) {
     const size_t frame_sz = (size_t)pw * ph;
@@ -231,14 +258,13 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
         const long long items = frame_sz / vec;
         const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
         const dim3 tgrid(gx, 1, 3), tblock(256);
-        if (false && vec == 4 && pf == 64) {   // full unrolling of the 64-bit lifting spills heavily: runtime loop is faster
-            auto kt = k_inv_t<WT, 4, 64>;
-            ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
-        } else if (vec == 4) {
-            auto kt = k_inv_t<WT, 4, 0>;
+        // (a fully unrolled PF = 64 instantiation spills 1.4-1.9 KB per thread and measured 2.3x slower than the
+        //  runtime loop, so the inverse t pass always uses PF = 0)
+        if (vec == 4) {
+            auto kt = k_inv_t<WT, 4, 0, WIDE>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
         } else {
-            auto kt = k_inv_t<WT, 2, 0>;
+            auto kt = k_inv_t<WT, 2, 0, WIDE>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
         }
     }
@@ -254,18 +280,29 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
     const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
     const int warps_per_block = 4;
     dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
-    auto kyx = k_inv_yx<WT, M>;
+    auto kyx = k_inv_yx<WT, M, WIDE>;
     ALICE_LAUNCH(kyx, grid, dim3(32 * warps_per_block), 0, st, d_coef, d_rgb, w, h, f, pw, ph, n_strips, n_segs,
                  seg_pairs, vec_ok);
 }
 
 void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f,
                      int pw, int ph, int pf, const int steps[3], cudaStream_t st) {
-    switch (wavelet) {
-    case WT_CDF53: launch_inv<WT_CDF53>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
-    case WT_CDF97: launch_inv<WT_CDF97>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
-    default:       launch_inv<WT_HAAR>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st); break;
+    bool narrow = true;   // every channel's coefficients stay within the 32-bit / i16 bounds above
+    for (int c = 0; c < 3; c++) {
+        const long long a = steps[c] < 0 ? -(long long)steps[c] : (long long)steps[c];
+        if (128 * a > kNarrowMaxCoef) narrow = false;
     }
+#define ALICE_INV(WT)                                                                                            \
+    do {                                                                                                         \
+        if (narrow) launch_inv<WT, false>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st);            \
+        else launch_inv<WT, true>(d_symbols, d_coef, d_rgb, w, h, f, pw, ph, pf, steps, st);                    \
+    } while (0)
+    switch (wavelet) {
+    case WT_CDF53: ALICE_INV(WT_CDF53); break;
+    case WT_CDF97: ALICE_INV(WT_CDF97); break;
+    default:       ALICE_INV(WT_HAAR); break;
+    }
+#undef ALICE_INV
 }
 
 }  // namespace alice

@@ -9,23 +9,28 @@
 // rANS is a serial recurrence on a 32-bit state and .alc carries no side information, so a
 // stream cannot be split bit-exactly: throughput comes from (a) the shortest possible
 // dependent chain per symbol and (b) hundreds of streams in flight (grid = streams of all
-// in-flight chunks).  Every thread of the warp executes the same recurrence on the same
-// values (the warp is a scalar engine with a 32-wide memory system): symbols, stream bytes
-// and output are moved 512 at a time by all lanes through shared-memory rings, so the
-// serial code touches only shared memory and registers.
+// in-flight chunks).  Each warp alternates between lane-parallel phases (all 32 lanes move
+// symbols, table entries, stream bytes and output through shared memory, 512 symbols at a
+// time) and a serial phase in which lane 0 alone runs the state recurrence out of shared
+// memory and registers (one active lane keeps every shared access a single wavefront).
+// profiles/r01_rans_stalls.md records the measurements behind these choices.
 //
-// Encoder step (src/rans.rs:269-285), branch-free for freq in (16, 4096]:
+// Encoder step (src/rans.rs:269-285), for freq in (16, 4096]:
 //     k  = x > freq*2^19 - 1                     (one renormalisation byte at most when freq > 16)
-//     q0 = floor(x / freq) = ((x*rcp + rcp) >> 32) >> sh      exact for x < 2^31 + 2^15
+//     q0 = floor(x / freq) = umulhi(x, rcp) >> sh             exact for x < 2^31 + 2^15
 //     q  = q0 >> 8k        because floor(floor(x / 256) / f) == floor(floor(x / f) / 256)
 //     x' = (x >> 8k) + cum + q * (4096 - freq)   == ((x>>8k) / f << 12) + (x>>8k) % f + cum
-// so the division does not wait for the renormalisation decision.  Symbols with freq <= 16,
-// freq > 4096 (the wrapped last symbol of a malformed table) or freq == 0 take a generic step.
+// so the division does not wait for the renormalisation decision; both outcomes are computed
+// and one is selected.  The serial loop only logs the state before each step; all lanes then
+// re-derive the emitted bytes from (state, limit) and write them.  Groups of 16 symbols that
+// contain a freq in [2, 16] run a two-byte variant; freq == 1, freq > 4096 (the u16-wrapped
+// last symbol of a malformed table) or freq == 0 take a literal step with a true division.
 //
-// Decoder step (src/rans.rs:351-371): symbol 0 owns slots [0, freq0), so the common case
-// needs no table access; other slots read {freq, slot - cum} from a 4096-entry shared table.
-// Stream bytes come from a shared "window" table holding, for every byte position, the next
-// four bytes as one big-endian word, so renormalisation is two predicated funnel shifts.
+// Decoder step (src/rans.rs:351-371): {freq, slot - cum} come from a 4096-entry shared table
+// whose address is taken from a second funnel shift ((x << 3) without waiting for x); stream
+// bytes come from a shared "window" table holding, for every byte position, the next eight
+// bytes as two big-endian words (8 bytes per position: the renormalisation shift in bits is
+// the address increment), so renormalisation is two selects and one funnel shift.
 #include "kernels.h"
 
 namespace alice {

@@ -30,8 +30,9 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 
 // WIDE = true : the reference's wrapping i32 arithmetic with the i64 lifting product, i32 hand-off (any header).
 // WIDE = false: 32-bit products and an i16 hand-off, exact while 128 * |quant_step| <= kNarrowMaxCoef (see launcher).
+// hand-off type between the t pass and the y/x pass: i32 in both variants (an i16 hand-off measured slower in
+// k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
 template <bool WIDE> struct Handoff { typedef int32_t T; };
-template <> struct Handoff<false> { typedef int16_t T; };
 
 template <int WT, int VEC, int PF, bool WIDE>
 __global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 3 : 4))
@@ -49,7 +50,7 @@ k_inv_t(const uint8_t *__restrict__ symbols, void *__restrict__ coef_v, int pw, 
     const long long n_items = (long long)(frame_sz / VEC);
 
     auto store_vec = [&](HT *p, const int (&v)[VEC]) {
-        if (WIDE) {
+        if (sizeof(HT) == 4) {
             if (VEC == 4) *reinterpret_cast<int4 *>(p) = make_int4(v[0], v[1], v[VEC - 2], v[VEC - 1]);
             else *reinterpret_cast<int2 *>(p) = make_int2(v[0], v[1]);
         } else {

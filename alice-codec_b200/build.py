@@ -40,13 +40,15 @@ def lib_path():
     return os.path.join(HERE, "lib", "libalice_codec.so")
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: experiment builds (lib/libalice_codec_<variant>.so compiled with extra -D flags); the product
+    library is the plain build."""
     out_dir = os.path.join(HERE, "lib")
-    obj_dir = os.path.join(out_dir, "obj")
+    obj_dir = os.path.join(out_dir, "obj" + ("_" + variant if variant else ""))
     os.makedirs(obj_dir, exist_ok=True)
-    stamp = os.path.join(out_dir, "build.sha256")
-    digest = _digest(_inputs() + [os.path.abspath(__file__)])
-    so = lib_path()
+    stamp = os.path.join(out_dir, "build" + ("_" + variant if variant else "") + ".sha256")
+    digest = _digest(_inputs() + [os.path.abspath(__file__)]) + "".join(defines)
+    so = lib_path() if not variant else os.path.join(out_dir, f"libalice_codec_{variant}.so")
     if not force and os.path.exists(so) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return so
     if not os.path.exists(NVCC):
@@ -54,7 +56,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ([NVCC] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", os.path.join(CSRC, src), "-o", obj])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
@@ -111,5 +114,7 @@ if __name__ == "__main__":
     ap.add_argument("--emul", action="store_true")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--variant", default=None, help="experiment build name (lib/libalice_codec_<variant>.so)")
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build_emul(a.force) if a.emul else build(a.force, a.verbose))
+    print(build_emul(a.force) if a.emul else build(a.force, a.verbose, a.variant, tuple(a.defines)))

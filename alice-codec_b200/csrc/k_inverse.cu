@@ -273,13 +273,19 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
     const int halfx = pw / 2, halfy = ph / 2;
     const int n_strips = (halfx + 30 * M - 1) / (30 * M);
     long long base_warps = (long long)n_strips * f;
-    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * 24 + base_warps - 1) / base_warps),
+#ifndef ALICE_YX_TARGET_WARPS
+#define ALICE_YX_TARGET_WARPS 96   // as in k_forward.cu: finer segments, one warp per block (1.88 -> 1.70 ms measured)
+#endif
+#ifndef ALICE_YX_WPB
+#define ALICE_YX_WPB 1
+#endif
+    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * ALICE_YX_TARGET_WARPS + base_warps - 1) / base_warps),
                                           std::max(1, halfy / 16));
     int seg_pairs = (halfy + n_segs - 1) / n_segs;
     n_segs = (halfy + seg_pairs - 1) / seg_pairs;
     const long long n_warps = (long long)n_strips * n_segs * f;
     const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
-    const int warps_per_block = 4;
+    const int warps_per_block = ALICE_YX_WPB;
     dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
     auto kyx = k_inv_yx<WT, M, WIDE>;
     ALICE_LAUNCH(kyx, grid, dim3(32 * warps_per_block), 0, st, d_coef, d_rgb, w, h, f, pw, ph, n_strips, n_segs,

@@ -17,9 +17,11 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--quality", type=int, default=80)
 ap.add_argument("--wavelet", default="cdf97")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--lib", default=None, help="experiment build of the library")
+ap.add_argument("--skip-rans", action="store_true", help="front-end / back-end kernels only (stage API)")
 a = ap.parse_args()
 pkg = load_package()
-api = pkg.default_api()
+api = pkg.Api(a.lib) if a.lib else pkg.default_api()
 api.set_device(0)
 st = torch.cuda.current_stream()
 n = a.width * a.height * a.frames * 3

@@ -77,6 +77,9 @@ SIGNATURES = {
     "alice_codec_encode_stages": (vp, [vp, u8p, u64, u32, u32, u32, i32p, u8p]),
     "alice_codec_decode_stages": (vp, [vp, u64p, u8p]),
     "alice_codec_batch_create": (vp, [u8, u8, u32, u32, u32, u32, vp]),
+    "alice_codec_batch_create_ex": (vp, [u8, u8, u32, u32, u32, u32, vp, u32]),
+    "alice_codec_batch_workspace_bytes": (u64, [vp]),
+    "alice_codec_batch_encode_device_ws": (cint, [vp, C.POINTER(vp), C.POINTER(vp), u32]),
     "alice_codec_batch_destroy": (None, [vp]),
     "alice_codec_batch_encode_device": (cint, [vp, C.POINTER(vp), u32]),
     "alice_codec_batch_decode_device": (cint, [vp, C.POINTER(vp), u32]),

@@ -424,12 +424,14 @@ class ChunkBatch:
     wraps the alice_codec_batch_* entry points.  Device pointers are plain integers
     (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t value (0 = default stream)."""
 
-    def __init__(self, quality, wavelet, width, height, frames, n_chunks, stream: int = 0, api: Api | None = None):
+    def __init__(self, quality, wavelet, width, height, frames, n_chunks, stream: int = 0, api: Api | None = None,
+                 shared_workspace: bool = False):
         self._api = api or default_api()
         self.n_chunks = n_chunks
         self.shape = (width, height, frames)
-        self._h = self._api.lib.alice_codec_batch_create(int(quality), _wavelet_byte(wavelet), width, height, frames,
-                                                         n_chunks, C.c_void_p(stream))
+        self.shared_workspace = shared_workspace
+        self._h = self._api.lib.alice_codec_batch_create_ex(int(quality), _wavelet_byte(wavelet), width, height, frames,
+                                                            n_chunks, C.c_void_p(stream), 1 if shared_workspace else 0)
         if not self._h:
             self._api._raise()
 
@@ -445,8 +447,17 @@ class ChunkBatch:
         arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
         return arr
 
-    def encode_device(self, d_rgb_ptrs):
+    def workspace_bytes(self):
+        return self._api.lib.alice_codec_batch_workspace_bytes(self._h)
+
+    def encode_device(self, d_rgb_ptrs, d_workspace_ptrs=None):
+        """d_workspace_ptrs: per-chunk buffers of workspace_bytes() (shared-workspace batches only); a workspace may
+        be the chunk's RGB input or the buffer it is decoded into later."""
         arr = self._ptr_array(d_rgb_ptrs)
+        if d_workspace_ptrs is not None:
+            ws = self._ptr_array(d_workspace_ptrs)
+            self._api._chk(self._api.lib.alice_codec_batch_encode_device_ws(self._h, arr, ws, len(d_rgb_ptrs)))
+            return
         self._api._chk(self._api.lib.alice_codec_batch_encode_device(self._h, arr, len(d_rgb_ptrs)))
 
     def decode_device(self, d_rgb_out_ptrs):

@@ -598,6 +598,10 @@ uint8_t *alice_codec_decode_stages(const EncodedChunk *chunk, uint64_t *out_len,
 // ------------------------------------------------------------------------------ batch API
 AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t w, uint32_t h, uint32_t f,
                                      uint32_t n_chunks, void *cuda_stream) {
+    return alice_codec_batch_create_ex(quality, wavelet, w, h, f, n_chunks, cuda_stream, 0);
+}
+AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32_t w, uint32_t h, uint32_t f,
+                                        uint32_t n_chunks, void *cuda_stream, uint32_t flags) {
     set_error(0, "");
     if (wavelet > 2 || n_chunks == 0) { set_error(kErrDimensions, "bad wavelet byte or n_chunks == 0"); return nullptr; }
     Dims d;
@@ -609,7 +613,8 @@ AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t 
     // single chunks keep the worst-case payload capacity; batches budget N/3 + 64 KiB per stream and fall
     // back to a worst-case buffer for any stream that overflows (Engine::run_rans_encode)
     const uint64_t cap = n_chunks == 1 ? 0 : d.padded / 3 + 65536;
-    b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false);
+    b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false,
+                                       (flags & ALICE_BATCH_SHARED_WORKSPACE) != 0);
     if (!b->eng || !b->eng->ok()) { delete b->eng; delete b; return nullptr; }
     b->quality = quality;
     b->wavelet = wavelet;
@@ -625,6 +630,14 @@ int alice_codec_batch_encode_device(AliceBatch *b, const uint8_t *const *d_rgb, 
     if (!b || !d_rgb) { set_error(kErrNull, "null argument"); return kErrNull; }
     return b->eng->encode_device(b->quality, b->wavelet, d_rgb, n, nullptr);
 }
+int alice_codec_batch_encode_device_ws(AliceBatch *b, const uint8_t *const *d_rgb, uint8_t *const *d_workspace,
+                                       uint32_t n) {
+    set_error(0, "");
+    if (!b || !d_rgb || !d_workspace) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!b->eng->shared_workspace()) { set_error(kErrDimensions, "batch was not created with ALICE_BATCH_SHARED_WORKSPACE"); return kErrDimensions; }
+    return b->eng->encode_device(b->quality, b->wavelet, d_rgb, n, nullptr, d_workspace);
+}
+uint64_t alice_codec_batch_workspace_bytes(const AliceBatch *b) { return b ? b->eng->workspace_bytes() : 0; }
 int alice_codec_batch_decode_device(AliceBatch *b, uint8_t *const *d_rgb_out, uint32_t n) {
     set_error(0, "");
     if (!b || !d_rgb_out) { set_error(kErrNull, "null argument"); return kErrNull; }
@@ -651,7 +664,9 @@ int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, ui
         b->stage_ptrs[i] = s;
         CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
     }
-    int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr);
+    // shared-workspace batches keep each chunk's symbol planes in its RGB staging buffer
+    int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr,
+                              e->shared_workspace() ? b->stage_ptrs.data() : nullptr);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++) {
         out_chunks[i] = alice_codec_batch_get_chunk(b, i);

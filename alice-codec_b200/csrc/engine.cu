@@ -201,8 +201,9 @@ template <class T> static bool dev_alloc(T *&p, size_t bytes, uint64_t &acc) {
 }
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStream_t user_stream, bool own_stream)
-    : d_(d), cap_(cap_chunks), own_stream_(own_stream) {
+Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStream_t user_stream, bool own_stream,
+               bool shared_workspace)
+    : d_(d), cap_(cap_chunks), own_stream_(own_stream), shared_ws_(shared_workspace) {
     const size_t N = (size_t)d_.padded;
     const size_t vol = (size_t)d_.f * d_.ph * d_.pw;
     pay_cap_ = payload_cap ? round_up((size_t)payload_cap, 16) : rans_enc_worst_case(N);
@@ -212,7 +213,7 @@ Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStr
     } else st_ = user_stream;
     bool a = true;
     a = a && dev_alloc(d_scratch_, vol * 3 * 4, dev_bytes_);
-    a = a && dev_alloc(d_symbols_, S * N, dev_bytes_);
+    if (!shared_ws_) a = a && dev_alloc(d_symbols_, S * N, dev_bytes_);
     a = a && dev_alloc(d_hist_, S * 256 * sizeof(unsigned), dev_bytes_);
     a = a && dev_alloc(d_enc_, S * 256 * sizeof(EncSym), dev_bytes_);
     a = a && dev_alloc(d_dec_lut_, S * kDecLutEntries * sizeof(uint32_t), dev_bytes_);
@@ -228,6 +229,9 @@ Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStr
     for (auto &e : ev_) a = a && cudaEventCreate(&e) == cudaSuccess;
     if (!a) { cudaGetLastError(); set_error(kErrCuda, "device or pinned memory allocation failed"); return; }
     overflow_bufs_.assign(S, nullptr);
+    sym_ptr_.assign(cap_, nullptr);
+    if (!shared_ws_)
+        for (uint32_t c = 0; c < cap_; c++) sym_ptr_[c] = d_symbols_ + (size_t)c * 3 * N;
     stream_off_.assign(S, 0);
     stream_len_.assign(S, 0);
     stream_base_.assign(S, nullptr);
@@ -266,7 +270,7 @@ bool Engine::ensure_pinned_payload(size_t bytes) {
 uint8_t *Engine::rgb_stage(uint32_t slot) {
     while (rgb_stage_.size() <= slot) {
         uint8_t *p = nullptr;
-        if (!dev_alloc(p, (size_t)d_.n_pixels * 3, dev_bytes_)) {
+        if (!dev_alloc(p, std::max((size_t)d_.n_pixels * 3, shared_ws_ ? (size_t)d_.padded * 3 : (size_t)0), dev_bytes_)) {
             set_error(kErrCuda, "device memory allocation failed (rgb staging)");
             return nullptr;
         }
@@ -279,7 +283,7 @@ int Engine::run_rans_encode(uint32_t n) {
     const size_t N = (size_t)d_.padded;
     const uint32_t S = n * 3;
     for (uint32_t s = 0; s < S; s++) {
-        h_enc_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+        h_enc_jobs_[s].symbols = sym_ptr_[s / 3] + (size_t)(s % 3) * N;
         h_enc_jobs_[s].n = N;
         h_enc_jobs_[s].out = d_payload_ + (size_t)s * pay_cap_;
         h_enc_jobs_[s].cap = pay_cap_;
@@ -324,8 +328,15 @@ int Engine::run_rans_encode(uint32_t n) {
 }
 
 int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const *d_rgb, uint32_t n,
-                          int32_t *d_coef_dump) {
+                          int32_t *d_coef_dump, uint8_t *const *d_work) {
     if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    if (shared_ws_) {
+        if (!d_work) { set_error(kErrNull, "shared-workspace batch: workspace pointers required"); return kErrNull; }
+        for (uint32_t c = 0; c < n; c++) {
+            if (!d_work[c]) { set_error(kErrNull, "null workspace pointer"); return kErrNull; }
+            sym_ptr_[c] = d_work[c];
+        }
+    }
     const size_t N = (size_t)d_.padded;
     const int step = quality_to_step(quality);
     last_wavelet = wavelet;
@@ -334,7 +345,7 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     CU_TRY(cudaMemsetAsync(d_hist_, 0, (size_t)n * 3 * 256 * sizeof(unsigned), st_));
     CU_TRY(cudaEventRecord(ev_[0], st_));
     for (uint32_t c = 0; c < n; c++)
-        forward_frontend(wavelet, d_rgb[c], reinterpret_cast<int16_t *>(d_scratch_), d_symbols_ + (size_t)c * 3 * N,
+        forward_frontend(wavelet, d_rgb[c], reinterpret_cast<int16_t *>(d_scratch_), sym_ptr_[c],
                          d_hist_ + (size_t)c * 3 * 256, (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph,
                          (int)d_.pf, step, c == 0 ? d_coef_dump : nullptr, st_);
     CU_TRY(cudaEventRecord(ev_[1], st_));
@@ -394,7 +405,7 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     for (uint32_t s = 0; s < S; s++) {
         h_dec_jobs_[s].in = stream_base_[s] + stream_off_[s];
         h_dec_jobs_[s].len = stream_len_[s];
-        h_dec_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+        h_dec_jobs_[s].symbols = sym_ptr_[s / 3] + (size_t)(s % 3) * N;
         h_dec_jobs_[s].n = N;
     }
     CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
@@ -402,7 +413,7 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     CU_TRY(cudaEventRecord(ev_[6], st_));
     const int steps[3] = {last_step, last_step, last_step};
     for (uint32_t c = 0; c < n; c++)
-        inverse_backend(last_wavelet, d_symbols_ + (size_t)c * 3 * N, reinterpret_cast<int32_t *>(d_scratch_),
+        inverse_backend(last_wavelet, sym_ptr_[c], reinterpret_cast<int32_t *>(d_scratch_),
                         d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
     CU_TRY(cudaEventRecord(ev_[7], st_));
     CU_TRY(cudaStreamSynchronize(st_));
@@ -415,6 +426,8 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
 
 int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out) {
     if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    if (shared_ws_)   // the symbol planes of chunk i live in its output buffer (>= workspace_bytes()) until the last kernel
+        for (uint32_t i = 0; i < n; i++) sym_ptr_[i] = d_rgb_out[i];
     const size_t N = (size_t)d_.padded;
     const uint32_t S = n * 3;
     // validation, in the reference's order (pipeline.rs:562-579)
@@ -468,7 +481,7 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             off += len;
             h_dec_jobs_[s].in = dst;
             h_dec_jobs_[s].len = len;
-            h_dec_jobs_[s].symbols = d_symbols_ + (size_t)s * N;
+            h_dec_jobs_[s].symbols = sym_ptr_[i] + (size_t)c * N;
             h_dec_jobs_[s].n = N;
         }
     }
@@ -482,7 +495,7 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
     for (uint32_t i = 0; i < n; i++) {
         const Chunk &ck = *chunks[i];
         const int steps[3] = {ck.ch[0].quant_step, ck.ch[1].quant_step, ck.ch[2].quant_step};
-        inverse_backend(ck.wavelet, d_symbols_ + (size_t)i * 3 * N, reinterpret_cast<int32_t *>(d_scratch_),
+        inverse_backend(ck.wavelet, sym_ptr_[i], reinterpret_cast<int32_t *>(d_scratch_),
                         d_rgb_out[i], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
     }
     CU_TRY(cudaEventRecord(ev_[7], st_));

@@ -81,8 +81,13 @@ struct EngineTimings { float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
 class Engine {
 public:
     // payload_cap_per_stream == 0 -> worst case 2N+4 bytes (rANS emits at most 2 bytes per symbol)
+    // shared_workspace: the engine owns no symbol planes; every chunk's planes live in a caller-provided buffer of
+    // workspace_bytes() (device-pointer calls; it may be the buffer the chunk is later decoded into) or in the
+    // chunk's RGB staging buffer (host-pointer calls)
     Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap_per_stream, cudaStream_t user_stream,
-           bool own_stream);
+           bool own_stream, bool shared_workspace = false);
+    uint64_t workspace_bytes() const { return 3 * d_.padded; }
+    bool shared_workspace() const { return shared_ws_; }
     ~Engine();
     bool ok() const { return ok_; }
     const Dims &dims() const { return d_; }
@@ -93,7 +98,7 @@ public:
     // Device-resident encode of n chunks (n <= cap).  d_rgb[i] are device pointers.
     // coef_dump: optional device i32 [3][N] for chunk 0 (parity tests).
     int encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const *d_rgb, uint32_t n,
-                      int32_t *d_coef_dump);
+                      int32_t *d_coef_dump, uint8_t *const *d_work = nullptr);
     // Fill a Chunk (headers + payload copied to the host) from the last encode_device.
     int fetch_chunk(uint32_t i, Chunk &out);
     // Decode the payloads the last encode_device left on the device.
@@ -104,7 +109,7 @@ public:
     // staging buffers for host-pointer entry points
     uint8_t *rgb_stage(uint32_t slot);          // device buffer of 3*n_pixels bytes, slot in [0, n_stage)
     uint32_t n_stage() const { return (uint32_t)rgb_stage_.size(); }
-    const uint8_t *symbols_dev(uint32_t chunk) const { return d_symbols_ + (size_t)chunk * 3 * d_.padded; }
+    const uint8_t *symbols_dev(uint32_t chunk) const { return sym_ptr_[chunk]; }
     EngineTimings timings;
     uint8_t last_wavelet = 0;
     int last_step = 1;
@@ -120,7 +125,9 @@ private:
     uint64_t dev_bytes_ = 0;
     // device
     void *d_scratch_ = nullptr;       // i16 planes (encode) / i32 coefficients (decode): 4 B * 3 * f*ph*pw
-    uint8_t *d_symbols_ = nullptr;    // [cap][3][N]
+    uint8_t *d_symbols_ = nullptr;    // [cap][3][N] (absent in shared-workspace mode)
+    std::vector<uint8_t *> sym_ptr_;  // per chunk: where its symbol planes [3][N] live
+    bool shared_ws_ = false;
     unsigned *d_hist_ = nullptr;      // [cap][3][256]
     EncSym *d_enc_ = nullptr;         // [cap*3][256]
     uint32_t *d_dec_lut_ = nullptr;   // [cap*3][4096]

@@ -205,10 +205,11 @@ def main():
     n_px = W * H * F
     rgb_bytes = 3 * n_px
     free_b, total_b = torch.cuda.mem_get_info()
-    # per chunk in flight: RGB in + RGB out (bench buffers) + symbols (3 B/px) + payload budget (1 B/px + 192 KiB)
-    per_chunk = 2 * rgb_bytes + 3 * n_px + n_px + 3 * 65536 + 3 * (16384 + 256 * 16 + 1024)
+    # per chunk in flight: RGB in + RGB out (bench buffers; the output buffer doubles as the chunk's symbol-plane
+    # workspace, ALICE_BATCH_SHARED_WORKSPACE) + payload budget (1 B/px + 192 KiB) + tables
+    per_chunk = 2 * rgb_bytes + n_px + 3 * 65536 + 3 * (16384 + 256 * 16 + 1024)
     fixed = 12 * n_px + (2 << 30)            # 4-byte scratch volume x 3 channels + head-room
-    B = args.chunks or max(1, min(120, int((free_b - fixed) // per_chunk)))
+    B = args.chunks or max(1, min(176, int((free_b - fixed) // per_chunk)))
     d_in = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
     d_out = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
     for i, t in enumerate(d_in):
@@ -216,13 +217,15 @@ def main():
         api._chk(api.lib.alice_codec_synth_rgb_device(1, SEED + rank + i * world, W, H, F, C.c_void_p(t.data_ptr()),
                                                       C.c_void_p(stream.cuda_stream)))
     torch.cuda.synchronize()
-    batch = pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, B, stream=stream.cuda_stream, api=api)
+    batch = pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, B, stream=stream.cuda_stream, api=api,
+                           shared_workspace=True)
+    assert batch.workspace_bytes() == rgb_bytes
     in_ptrs = [t.data_ptr() for t in d_in]
     out_ptrs = [t.data_ptr() for t in d_out]
 
     def step():
-        batch.encode_device(in_ptrs)
-        batch.decode_device(out_ptrs)
+        batch.encode_device(in_ptrs, out_ptrs)     # symbol planes of chunk i live in its output buffer ...
+        batch.decode_device(out_ptrs)              # ... until the decode back-end overwrites them with RGB
 
     def barrier():
         if world > 1:
@@ -339,7 +342,7 @@ def main():
         shares = [list(range(t, Be, T)) for t in range(T)]
         streams = [torch.cuda.Stream() for _ in range(T)]
         batches = [pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, len(shares[t]), stream=streams[t].cuda_stream,
-                                  api=api) for t in range(T)]
+                                  api=api, shared_workspace=True) for t in range(T)]
         payload = [0] * T
         t_start, t_end = [0.0] * T, [0.0] * T
         go = threading.Barrier(T + 1)

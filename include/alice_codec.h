@@ -149,6 +149,17 @@ typedef struct AliceBatch AliceBatch;
 /* cuda_stream: a cudaStream_t (may be null = the legacy default stream) on which all work is issued */
 AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t width, uint32_t height,
                                      uint32_t frames, uint32_t n_chunks, void *cuda_stream);
+/* flags: ALICE_BATCH_SHARED_WORKSPACE — the batch owns no symbol planes (3 bytes per padded pixel and chunk): with
+ * device pointers the caller passes one workspace of alice_codec_batch_workspace_bytes() per chunk to
+ * alice_codec_batch_encode_device_ws (it may be the chunk's RGB input itself, or the buffer the chunk is decoded
+ * into later: decode finishes reading the planes before it writes RGB); with host pointers the batch's RGB staging
+ * buffers double as the workspace.  Saves 3 B/px of device memory per chunk in flight. */
+enum { ALICE_BATCH_SHARED_WORKSPACE = 1 };
+AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32_t width, uint32_t height,
+                                        uint32_t frames, uint32_t n_chunks, void *cuda_stream, uint32_t flags);
+uint64_t alice_codec_batch_workspace_bytes(const AliceBatch *b);
+int alice_codec_batch_encode_device_ws(AliceBatch *b, const uint8_t *const *d_rgb, uint8_t *const *d_workspace,
+                                       uint32_t n);
 void alice_codec_batch_destroy(AliceBatch *b);
 /* d_rgb[i]: device pointer to chunk i's interleaved RGB (3*w*h*f bytes).  Runs front-end, table build and
  * all 3*n rANS streams; results stay on the device.  Synchronises the stream before returning. */

@@ -289,3 +289,50 @@ def check_reference_abi(api):
         for n_ in (0, 1, 2, 3, 9, 64):
             x = (np.arange(n_, dtype=np.int32) * 37 - 100) % 251
             assert np.array_equal(api.wavelet1d(wv, x), O.wavelet1d_forward(wv, x))
+
+
+def check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5)), n=3):
+    """ALICE_BATCH_SHARED_WORKSPACE: symbol planes live in caller buffers (device API; here the decode outputs and,
+    for one chunk, the RGB input itself) or in the staging buffers (host API).  Needs torch for device memory."""
+    import torch
+    for (w, h, f) in shapes:
+        for q, wv in ((80, 1), (90, 0)):
+            rgbs = [O.generate(O.G1 if i else O.G2, w, h, f, O.SEED + i) for i in range(n)]
+            refs = [O.encode(r, w, h, f, q, wv) for r in rgbs]
+            outs_ref = [O.decode(r) for r in refs]
+            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=0, api=api, shared_workspace=True)
+            ws = batch.workspace_bytes()
+            pw, ph, pf = O.padded_dims(w, h, f)
+            assert ws == 3 * pw * ph * pf
+            dev = "cuda" if torch.cuda.is_available() else "cpu"        # the emulator treats host memory as device memory
+            d_in = [torch.zeros(max(ws, r.size), dtype=torch.uint8, device=dev) for r in rgbs]
+            for t, r in zip(d_in, rgbs):
+                t[:r.size] = torch.from_numpy(r).to(dev)
+            d_out = [torch.zeros(max(ws, r.size), dtype=torch.uint8, device=dev) for r in rgbs]
+            work = [d_out[0], d_out[1], d_in[2]]                         # chunk 2: in place over its own input
+            batch.encode_device([t.data_ptr() for t in d_in], [t.data_ptr() for t in work])
+            for i in range(n):
+                assert batch.get_chunk(i).to_bytes() == refs[i], (w, h, f, q, wv, i)
+            batch.decode_device([t.data_ptr() for t in work])            # decode over the workspaces
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            for i in range(n):
+                assert np.array_equal(work[i][:rgbs[i].size].cpu().numpy(), outs_ref[i]), (w, h, f, q, wv, i)
+            # host API: staging buffers double as the workspace
+            h_in = [torch.from_numpy(r.copy()) for r in rgbs]
+            h_out = [torch.zeros(r.size, dtype=torch.uint8) for r in rgbs]
+            if dev == "cuda":
+                h_in = [t.pin_memory() for t in h_in]
+                h_out = [t.pin_memory() for t in h_out]
+            chunks = batch.encode_host([t.data_ptr() for t in h_in])
+            assert [c.to_bytes() for c in chunks] == refs
+            batch.decode_host(chunks, [t.data_ptr() for t in h_out])
+            for i in range(n):
+                assert np.array_equal(h_out[i].numpy(), outs_ref[i])
+            # a plain batch refuses the workspace call; a shared one refuses to run without workspaces
+            try:
+                batch.encode_device([t.data_ptr() for t in d_in])
+                raise AssertionError("workspace pointers required")
+            except pkg.CodecError as e:
+                assert e.kind == "NullArgument"
+            batch.close()

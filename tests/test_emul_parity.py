@@ -58,3 +58,7 @@ def test_errors_and_abi(api):
     parity.check_errors(api)
     parity.check_reference_abi(api)
     parity.check_decode_foreign_headers(api, np.random.default_rng(3))
+
+
+def test_shared_workspace_batch(api):
+    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5)), n=3)

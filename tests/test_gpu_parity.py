@@ -208,6 +208,10 @@ def test_batch_api_device_and_host(api):
         batch.close()
 
 
+def test_shared_workspace_batch(api):
+    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5), (256, 64, 64)), n=3)
+
+
 def test_synth_on_device_matches_oracle_generators(api):
     import ctypes as C
     import torch

@@ -369,10 +369,11 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
 }
 
 // --------------------------------------------------------------------------------- decode
-constexpr int kDecBlock = 512;                   // symbols per fast block (one 16-byte store per lane)
-constexpr int kWinPos = 2048;                    // byte positions held by the window ring
+constexpr int kDecBlock = 256;                   // symbols per fast block (one 8-byte store per lane)
+constexpr int kWinPos = 1024;                    // byte positions held by the window ring
 constexpr int kWinMirror = 2 * kDecBlock + 16;   // positions mirrored past the end: a block reads linearly
-constexpr int kWinFill = 512;                    // bytes converted per refill (16 per lane)
+constexpr int kWinFill = 256;                    // bytes converted per refill (8 per lane)
+// (48.9 KB per block in total, so four decode blocks fit the 227 KB of an SM: 592 concurrent streams)
 // window entry of position p: {bytes p..p+3, bytes p+4..p+7} as two big-endian words; 8 bytes per position makes
 // the renormalisation shift (8 bits per byte) equal to the address increment
 constexpr int kDecSmemBytes = kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
@@ -479,22 +480,22 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         while (filled < o + 2ull * kDecBlock + 12) {
             __syncwarp();
             {
-                const unsigned long long base = filled + 16ull * lane;
-                uint32_t d[6];
+                const unsigned long long base = filled + 8ull * lane;
+                uint32_t d[4];
                 if (base < end_off) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ga + base));
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-                } else { d[0] = d[1] = d[2] = d[3] = 0; }
-                if (base + 16 < end_off) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base + 16));
-                    d[4] = v.x; d[5] = v.y;
-                } else { d[4] = d[5] = 0; }
-                uint32_t be[20];   // be[k] = big-endian word of bytes base+k .. base+k+3
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base));
+                    d[0] = v.x; d[1] = v.y;
+                } else { d[0] = d[1] = 0; }
+                if (base + 8 < end_off) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base + 8));
+                    d[2] = v.x; d[3] = v.y;
+                } else { d[2] = d[3] = 0; }
+                uint32_t be[12];   // be[k] = big-endian word of bytes base+k .. base+k+3
 #pragma unroll
-                for (int k = 0; k < 20; k++)
-                    be[k] = __byte_perm(__funnelshift_r(d[k >> 2], d[(k >> 2) + 1 > 5 ? 5 : (k >> 2) + 1], 8 * (k & 3)), 0, 0x0123);
+                for (int k = 0; k < 12; k++)
+                    be[k] = __byte_perm(__funnelshift_r(d[k >> 2], d[(k >> 2) + 1 > 3 ? 3 : (k >> 2) + 1], 8 * (k & 3)), 0, 0x0123);
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
+                for (int k = 0; k < 8; k++) {
                     const uint32_t idx = (uint32_t)((base + k) & (kWinPos - 1));
                     const uint2 e = make_uint2(be[k], be[k + 4]);
                     win[idx] = e;
@@ -540,19 +541,18 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         s.x = x;
         s.pos += (unsigned long long)(wa - wa0) / 8;
         __syncwarp();
-        // ---- all lanes: slot -> symbol for 16 symbols each, one 16-byte store per lane
+        // ---- all lanes: slot -> symbol for 8 symbols each, one 8-byte store per lane
         {
-            const uint4 sv0 = *reinterpret_cast<const uint4 *>(slots + 16 * lane);
-            const uint4 sv1 = *reinterpret_cast<const uint4 *>(slots + 16 * lane + 8);
-            const uint32_t sw[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
-            uint32_t ow[4];
+            const uint4 sv = *reinterpret_cast<const uint4 *>(slots + 8 * lane);
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            uint32_t ow[2];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < 2; k++) {
                 const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> 3], b2 = symt[sw[2 * k] >> 19];
                 const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> 3], d2 = symt[sw[2 * k + 1] >> 19];
                 ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
             }
-            *reinterpret_cast<uint4 *>(out + i + 16 * lane) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *reinterpret_cast<uint2 *>(out + i + 8 * lane) = make_uint2(ow[0], ow[1]);
         }
         __syncwarp();
         i += kDecBlock;

@@ -327,7 +327,7 @@ def main():
         try:                                            # pinned RGB in + out must fit the host comfortably (all ranks)
             import psutil
             host_avail = psutil.virtual_memory().available
-            Be = max(1, min(Be, int(host_avail * 0.5 / world // (2 * rgb_bytes))))
+            Be = max(1, min(Be, int(host_avail * 0.6 / world // (2 * rgb_bytes))))
         except Exception:  # noqa: BLE001
             Be = min(Be, 32)
         T = max(1, min(args.e2e_threads, Be))
@@ -361,6 +361,7 @@ def main():
                 tb = time.perf_counter()
                 payload[t] = sum(c.compressed_size + 3138 for c in chunks)
                 batches[t].decode_host(chunks, hout)    # H2D payload, kernels, D2H RGB
+                del chunks                              # payload buffers go back to the library's pinned pool
                 tc = time.perf_counter()
                 if args.verbose:
                     sys.stderr.write(f"[e2e] thread {t} it {it}: encode_host {tb - ta:.2f} s, decode_host {tc - tb:.2f} s\n")

@@ -152,9 +152,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=0, help="chunks in flight per GPU (0 = sized from free HBM)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (0 = same as --chunks)")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-threads", type=int, default=3)
-    ap.add_argument("--e2e-stagger", type=float, default=0.0, help="seconds between the first starts of the e2e host threads")
+    ap.add_argument("--e2e-stagger", type=float, default=2.3, help="seconds between the first starts of the e2e host threads")
     ap.add_argument("--ref-frames", type=int, default=16)
     ap.add_argument("--cpu-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")

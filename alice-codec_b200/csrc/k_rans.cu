@@ -162,19 +162,28 @@ constexpr int kEncBlock = 512;                  // symbols per warp-wide fetch (
 constexpr int kEncRing = 2 * kEncBlock + 64;    // bytes one block can emit (2 per symbol) + the 4 state bytes + slack
 constexpr uint32_t kGrpSmall = 1u, kGrpGeneric = 2u;
 
-__global__ void ALICE_LAUNCH_BOUNDS(32, 1)
+// Streams per block: four warps = one per SM sub-partition, so that the streams of concurrent launches (several
+// batches in flight) spread evenly over the warp schedulers instead of piling up single-warp blocks on a few of them.
+constexpr int kLanesPerBlock = 4;
+constexpr int kEncSmemPerWarp = 256 * 16 + kEncBlock * (16 + 4 + 4 + 1) + 32 * 4 + kEncRing;   // 18 112 bytes
+static_assert(kEncSmemPerWarp % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+
+__global__ void ALICE_LAUNCH_BOUNDS(32 * kLanesPerBlock, 1)
 k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ enc_all,
-              unsigned long long *__restrict__ results) {
-    __shared__ uint4 tab[256];                       // EncSym of every symbol
+              unsigned long long *__restrict__ results, int n_streams) {
+    ALICE_DYN_SMEM(smem_all);
+    const int stream = blockIdx.x * kLanesPerBlock + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kEncSmemPerWarp;
+    uint4 *tab = reinterpret_cast<uint4 *>(smem);                                   // EncSym of every symbol
     // staged per symbol of the block, indexed [b][lane] (symbol b of lane's group): conflict-free for the lanes
-    __shared__ uint4 st_a[kEncBlock];                // {x_lim, rcp, cmpl, cum}
-    __shared__ uint32_t st_s[kEncBlock];             // division shift sh | (freq <= 16) << 8
-    __shared__ uint32_t st_x[kEncBlock];             // state before the step of each symbol
-    __shared__ uint32_t grp[32];                     // per group of 16 symbols: kGrpSmall | kGrpGeneric
-    __shared__ uint8_t st_sym[kEncBlock];            // the symbols themselves (generic path)
-    __shared__ __align__(16) uint8_t ring[kEncRing]; // emitted bytes of the block, filled from the top down
-    const int stream = blockIdx.x;
-    const int lane = threadIdx.x;
+    uint4 *st_a = tab + 256;                                                        // {x_lim, rcp, cmpl, cum}
+    uint32_t *st_s = reinterpret_cast<uint32_t *>(st_a + kEncBlock);                // division shift sh | (freq <= 16) << 8
+    uint32_t *st_x = st_s + kEncBlock;                                              // state before the step of each symbol
+    uint32_t *grp = st_x + kEncBlock;                                               // per group of 16 symbols: kGrpSmall | kGrpGeneric
+    uint8_t *ring = reinterpret_cast<uint8_t *>(grp + 32);                          // emitted bytes of the block, filled from the top down
+    uint8_t *st_sym = ring + kEncRing;                                              // the symbols themselves (generic path)
+    const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(enc_all + (size_t)stream * 256);
@@ -365,7 +374,16 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
 void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *, unsigned long long *d_results,
                  int n_streams, cudaStream_t st) {
     if (n_streams <= 0) return;
-    ALICE_LAUNCH(k_rans_encode, dim3(n_streams), dim3(32), 0, st, d_jobs, d_enc, d_results);
+    const int smem = kLanesPerBlock * kEncSmemPerWarp;
+#ifndef ALICE_EMUL
+    static bool attr_set = false;   // idempotent; a race only repeats the call
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_rans_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+#endif
+    ALICE_LAUNCH(k_rans_encode, dim3((n_streams + kLanesPerBlock - 1) / kLanesPerBlock), dim3(32 * kLanesPerBlock), smem, st,
+                 d_jobs, d_enc, d_results, n_streams);
 }
 
 // --------------------------------------------------------------------------------- decode
@@ -399,16 +417,18 @@ ALICE_D uint32_t dec_step_generic(DecState &s, const uint2 *ent, const uint8_t *
     return sym;
 }
 
-__global__ void ALICE_LAUNCH_BOUNDS(32, 1)
+__global__ void ALICE_LAUNCH_BOUNDS(32 * kLanesPerBlock, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
-              const DecAux *__restrict__ aux_all) {
-    ALICE_DYN_SMEM(smem);
+              const DecAux *__restrict__ aux_all, int n_streams) {
+    ALICE_DYN_SMEM(smem_all);
+    const int stream = blockIdx.x * kLanesPerBlock + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kDecSmemBytes;
     uint2 *ent = reinterpret_cast<uint2 *>(smem);                               // slot -> {freq, slot - cum}
     uint2 *win = reinterpret_cast<uint2 *>(smem + kDecLutEntries * 8);          // position -> next 8 bytes, big-endian
     uint8_t *symt = smem + kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8;     // slot -> symbol
     uint16_t *slots = reinterpret_cast<uint16_t *>(symt + kDecLutEntries);      // slots decoded in this block
-    const int stream = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
     {
         const uint32_t *src = lut_all + (size_t)stream * kDecLutEntries;
@@ -565,11 +585,12 @@ void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecA
 #ifndef ALICE_EMUL
     static bool attr_set = false;   // idempotent; a race only repeats the call
     if (!attr_set) {
-        cudaFuncSetAttribute(k_rans_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes);
+        cudaFuncSetAttribute(k_rans_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kLanesPerBlock * kDecSmemBytes);
         attr_set = true;
     }
 #endif
-    ALICE_LAUNCH(k_rans_decode, dim3(n_streams), dim3(32), kDecSmemBytes, st, d_jobs, d_dec_lut, d_aux);
+    ALICE_LAUNCH(k_rans_decode, dim3((n_streams + kLanesPerBlock - 1) / kLanesPerBlock), dim3(32 * kLanesPerBlock),
+                 kLanesPerBlock * kDecSmemBytes, st, d_jobs, d_dec_lut, d_aux, n_streams);
 }
 
 }  // namespace alice

@@ -364,7 +364,9 @@ def main():
                 del chunks                              # payload buffers go back to the library's pinned pool
                 tc = time.perf_counter()
                 if args.verbose:
-                    sys.stderr.write(f"[e2e] thread {t} it {it}: encode_host {tb - ta:.2f} s, decode_host {tc - tb:.2f} s\n")
+                    ms = batches[t].timings()
+                    sys.stderr.write(f"[e2e] thread {t} it {it}: encode_host {tb - ta:.2f} s (fe {ms[0] / 1e3:.2f} rans {ms[2] / 1e3:.2f}), "
+                                     f"decode_host {tc - tb:.2f} s (rans {ms[4] / 1e3:.2f} be {ms[5] / 1e3:.2f})\n")
             t_end[t] = time.perf_counter()
         threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
         for th in threads:

@@ -158,21 +158,30 @@ void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *
 }
 
 // --------------------------------------------------------------------------------- encode
+template <int V> struct IntC { static constexpr int value = V; };
+// single-warp blocks when the launch alone gives every warp scheduler of the GPU a stream, else four warps per block
+template <class F> static void launch_lanes(int n_streams, F f) {
+    if (n_streams >= 2 * kNumSMs) f(IntC<1>());
+    else f(IntC<4>());
+}
+
 constexpr int kEncBlock = 512;                  // symbols per warp-wide fetch (16 bytes per lane)
 constexpr int kEncRing = 2 * kEncBlock + 64;    // bytes one block can emit (2 per symbol) + the 4 state bytes + slack
 constexpr uint32_t kGrpSmall = 1u, kGrpGeneric = 2u;
 
-// Streams per block: four warps = one per SM sub-partition, so that the streams of concurrent launches (several
-// batches in flight) spread evenly over the warp schedulers instead of piling up single-warp blocks on a few of them.
-constexpr int kLanesPerBlock = 4;
+// Streams per block (LPB): with four warps per block = one per SM sub-partition the streams of concurrent launches
+// (several batches in flight) spread evenly over the warp schedulers instead of piling up single-warp blocks on a
+// few of them (measured: encode 2.95-3.7 s -> 2.55-2.9 s with three batches in flight).  A launch that fills the
+// machine on its own uses single-warp blocks, which measured 6-11 % faster there (decode 3.66 s vs 4.06 s).
 constexpr int kEncSmemPerWarp = 256 * 16 + kEncBlock * (16 + 4 + 4 + 1) + 32 * 4 + kEncRing;   // 18 112 bytes
 static_assert(kEncSmemPerWarp % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
-__global__ void ALICE_LAUNCH_BOUNDS(32 * kLanesPerBlock, 1)
+template <int LPB>
+__global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ enc_all,
               unsigned long long *__restrict__ results, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
-    const int stream = blockIdx.x * kLanesPerBlock + (threadIdx.x >> 5);
+    const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
     if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
     unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kEncSmemPerWarp;
     uint4 *tab = reinterpret_cast<uint4 *>(smem);                                   // EncSym of every symbol
@@ -374,16 +383,19 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
 void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *, unsigned long long *d_results,
                  int n_streams, cudaStream_t st) {
     if (n_streams <= 0) return;
-    const int smem = kLanesPerBlock * kEncSmemPerWarp;
+    launch_lanes(n_streams, [&](auto lpb) {
+        constexpr int LPB = decltype(lpb)::value;
+        const int smem = LPB * kEncSmemPerWarp;
 #ifndef ALICE_EMUL
-    static bool attr_set = false;   // idempotent; a race only repeats the call
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_rans_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+        static bool attr_set = false;   // idempotent; a race only repeats the call
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_rans_encode<LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
 #endif
-    ALICE_LAUNCH(k_rans_encode, dim3((n_streams + kLanesPerBlock - 1) / kLanesPerBlock), dim3(32 * kLanesPerBlock), smem, st,
-                 d_jobs, d_enc, d_results, n_streams);
+        auto k = k_rans_encode<LPB>;
+        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);
+    });
 }
 
 // --------------------------------------------------------------------------------- decode
@@ -417,11 +429,12 @@ ALICE_D uint32_t dec_step_generic(DecState &s, const uint2 *ent, const uint8_t *
     return sym;
 }
 
-__global__ void ALICE_LAUNCH_BOUNDS(32 * kLanesPerBlock, 1)
+template <int LPB>
+__global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
               const DecAux *__restrict__ aux_all, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
-    const int stream = blockIdx.x * kLanesPerBlock + (threadIdx.x >> 5);
+    const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
     if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
     unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kDecSmemBytes;
     uint2 *ent = reinterpret_cast<uint2 *>(smem);                               // slot -> {freq, slot - cum}
@@ -582,15 +595,19 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
                  cudaStream_t st) {
     if (n_streams <= 0) return;
+    launch_lanes(n_streams, [&](auto lpb) {
+        constexpr int LPB = decltype(lpb)::value;
+        const int smem = LPB * kDecSmemBytes;
 #ifndef ALICE_EMUL
-    static bool attr_set = false;   // idempotent; a race only repeats the call
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_rans_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kLanesPerBlock * kDecSmemBytes);
-        attr_set = true;
-    }
+        static bool attr_set = false;   // idempotent; a race only repeats the call
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_rans_decode<LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
 #endif
-    ALICE_LAUNCH(k_rans_decode, dim3((n_streams + kLanesPerBlock - 1) / kLanesPerBlock), dim3(32 * kLanesPerBlock),
-                 kLanesPerBlock * kDecSmemBytes, st, d_jobs, d_dec_lut, d_aux, n_streams);
+        auto k = k_rans_decode<LPB>;
+        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
+    });
 }
 
 }  // namespace alice

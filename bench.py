@@ -336,6 +336,19 @@ def main():
         for i in range(Be):
             h_in[i].copy_(d_in[i])
         torch.cuda.synchronize()
+        # link probe: one pinned chunk each way, three times (explains run-to-run differences of the e2e figure)
+        link = {}
+        for name, fn in (("h2d", lambda: d_in[0].copy_(h_in[0], non_blocking=True)),
+                         ("d2h", lambda: h_out[0].copy_(d_out[0], non_blocking=True))):
+            fn()
+            torch.cuda.synchronize()
+            tp0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            link[name + "_gbs"] = round(3 * rgb_bytes / (time.perf_counter() - tp0) / 1e9, 1)
+        h_in[0].copy_(d_in[0])                          # restore nothing: d_in[0] was overwritten with its own data
+        torch.cuda.synchronize()
         batch.close()
         del d_in, d_out, in_ptrs, out_ptrs
         torch.cuda.empty_cache()
@@ -391,7 +404,7 @@ def main():
                "h2d_bytes_per_step": Be * rgb_bytes + sum(payload), "d2h_bytes_per_step": Be * rgb_bytes + sum(payload),
                "chunks_per_step_per_gpu": Be, "host_threads": T, "ms_per_step": round(1000 * dt / args.e2e_steps, 1),
                "timed_with": "host wall clock around synchronous C-ABI batch calls (pinned host buffers)",
-               "decoded_matches_oracle_digest": e2e_ok}
+               "decoded_matches_oracle_digest": e2e_ok, "pinned_link_probe": link}
         for bt in batches:
             bt.close()
         del h_in, h_out

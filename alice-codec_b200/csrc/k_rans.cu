@@ -385,7 +385,10 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
     if (n_streams <= 0) return;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        const int smem = LPB * kEncSmemPerWarp;
+        // a four-warp block asks for more than half an SM's shared memory, so no SM hosts two of them: the encoder
+        // step keeps a warp scheduler ~45 % busy and two streams per scheduler (block stacking under concurrent
+        // launches) measured up to 2x slower; a four-warp decode block (195 KB) is exclusive anyway
+        const int smem = LPB == 1 ? kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024);
 #ifndef ALICE_EMUL
         static bool attr_set = false;   // idempotent; a race only repeats the call
         if (!attr_set) {

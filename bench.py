@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--lib", default=None, help="experiment build of libalice_codec (debugging aid)")
     ap.add_argument("--e2e-only", action="store_true", help="skip the device-resident timed region (debug)")
     ap.add_argument("--quality", type=int, default=QUALITY)
     ap.add_argument("--wavelet", default=WAVELET)
@@ -198,7 +199,7 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    api = pkg.default_api()
+    api = pkg.Api(args.lib) if args.lib else pkg.default_api()
     api.set_device(local)
     stream = torch.cuda.current_stream()
 

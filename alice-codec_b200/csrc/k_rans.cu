@@ -159,6 +159,17 @@ void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *
 
 // --------------------------------------------------------------------------------- encode
 template <int V> struct IntC { static constexpr int value = V; };
+#ifndef ALICE_EMUL
+// opt-in to > 48 KB of dynamic shared memory: a per-device function attribute, set once per device and kernel
+template <class K> static void ensure_dyn_smem(K kernel, int bytes, unsigned long long &done_mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask & bit) return;   // idempotent; a race only repeats the call
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done_mask |= bit;
+}
+#endif
 // single-warp blocks when the launch alone gives every warp scheduler of the GPU a stream, else four warps per block
 template <class F> static void launch_lanes(int n_streams, F f) {
     if (n_streams >= 2 * kNumSMs) f(IntC<1>());
@@ -392,11 +403,8 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
         //  encode 2.8-2.95 s, decode 3.8-4.3 s vs 2.5-2.9 s and 4.04 s)
         const int smem = LPB == 1 ? kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024);
 #ifndef ALICE_EMUL
-        static bool attr_set = false;   // idempotent; a race only repeats the call
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_rans_encode<LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_set = true;
-        }
+        static unsigned long long attr_done = 0;
+        ensure_dyn_smem(k_rans_encode<LPB>, smem, attr_done);
 #endif
         auto k = k_rans_encode<LPB>;
         ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);
@@ -604,11 +612,8 @@ void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecA
         constexpr int LPB = decltype(lpb)::value;
         const int smem = LPB * kDecSmemBytes;
 #ifndef ALICE_EMUL
-        static bool attr_set = false;   // idempotent; a race only repeats the call
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_rans_decode<LPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_set = true;
-        }
+        static unsigned long long attr_done = 0;
+        ensure_dyn_smem(k_rans_decode<LPB>, smem, attr_done);
 #endif
         auto k = k_rans_decode<LPB>;
         ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);

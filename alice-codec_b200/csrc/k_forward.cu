@@ -233,8 +233,11 @@ ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
     return (uint32_t)s & 0xffu;
 }
 
+#ifndef ALICE_T_MINBLOCKS
+#define ALICE_T_MINBLOCKS 4
+#endif
 template <int WT, int VEC, int PF>
-__global__ void ALICE_LAUNCH_BOUNDS(256, 4)
+__global__ void ALICE_LAUNCH_BOUNDS(256, ALICE_T_MINBLOCKS)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
               int pw, int ph, int f, int pf, QuantDev q, int32_t *__restrict__ coef_dump) {
     constexpr int NST = WaveletTraits<WT>::NST;

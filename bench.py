@@ -328,7 +328,7 @@ def main():
         try:                                            # pinned RGB in + out must fit the host comfortably (all ranks)
             import psutil
             host_avail = psutil.virtual_memory().available
-            Be = max(1, min(Be, int(host_avail * 0.6 / world // (2 * rgb_bytes))))
+            Be = max(1, min(Be, int(host_avail * (0.6 if world == 1 else 0.5) / world // (2 * rgb_bytes))))
         except Exception:  # noqa: BLE001
             Be = min(Be, 32)
         T = max(1, min(args.e2e_threads, Be))

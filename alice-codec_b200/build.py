@@ -80,17 +80,20 @@ def emul_lib_path():
     return os.path.join(ROOT, "tests", "emul", "_build", "libalice_codec_emul.so")
 
 
-def build_emul(force=False):
+def build_emul(force=False, variant=None, defines=()):
+    """variant/defines: emulator builds of experiment variants (tests/emul/_build/<variant>/)."""
     out_dir = os.path.dirname(emul_lib_path())
+    if variant:
+        out_dir = os.path.join(out_dir, variant)
     os.makedirs(out_dir, exist_ok=True)
     stamp = os.path.join(out_dir, "build.sha256")
     emul_h = os.path.join(ROOT, "tests", "emul", "cuda_emul.h")
-    digest = _digest(_inputs() + [emul_h, os.path.abspath(__file__)])
-    so = emul_lib_path()
+    digest = _digest(_inputs() + [emul_h, os.path.abspath(__file__)]) + "".join(defines)
+    so = os.path.join(out_dir, os.path.basename(emul_lib_path()))
     if not force and os.path.exists(so) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return so
     flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-fwrapv", "-DALICE_EMUL", "-x", "c++", "-Wno-unknown-pragmas",
-             "-I", os.path.join(ROOT, "tests", "emul"), "-fvisibility=hidden"]
+             "-I", os.path.join(ROOT, "tests", "emul"), "-fvisibility=hidden"] + ["-D" + d for d in defines]
 
     def compile_one(src):
         obj = os.path.join(out_dir, src.replace(".cu", ".o"))
@@ -117,4 +120,4 @@ if __name__ == "__main__":
     ap.add_argument("--variant", default=None, help="experiment build name (lib/libalice_codec_<variant>.so)")
     ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build_emul(a.force) if a.emul else build(a.force, a.verbose, a.variant, tuple(a.defines)))
+    print(build_emul(a.force, a.variant, tuple(a.defines)) if a.emul else build(a.force, a.verbose, a.variant, tuple(a.defines)))

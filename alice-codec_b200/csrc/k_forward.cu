@@ -236,6 +236,11 @@ ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
 #ifndef ALICE_T_MINBLOCKS
 #define ALICE_T_MINBLOCKS 4
 #endif
+// 1: the compile-time-depth variant of k_fwd_t_quant runs a rolled, software-pipelined steady-state loop (20-31 KB of
+// code) instead of the fully unrolled one (122 KB, four times the instruction cache).  Unmeasured so far, hence off.
+#ifndef ALICE_T_ROLLED
+#define ALICE_T_ROLLED 0
+#endif
 template <int WT, int VEC, int PF>
 __global__ void ALICE_LAUNCH_BOUNDS(256, ALICE_T_MINBLOCKS)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
@@ -286,25 +291,88 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
         const size_t off = (size_t)item * VEC;
         FwdLift<WT, false> L[VEC];
         int k = 0;
+        // rows 2j and 2j+1 of this thread's VEC columns, as raw i16 pairs (padded frames re-read frame f-1,
+        // pipeline.rs:107-112)
+        struct RawPair { uint32_t a[VEC / 2], b[VEC / 2]; };
+        auto load_pair = [&](int j) {
+            const int t0 = min(2 * j, f - 1), t1 = min(2 * j + 1, f - 1);
+            RawPair r;
+            if (VEC == 4) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t0 * frame_sz + off));
+                const uint2 b = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t1 * frame_sz + off));
+                r.a[0] = a.x; r.a[VEC / 2 - 1] = a.y;
+                r.b[0] = b.x; r.b[VEC / 2 - 1] = b.y;
+            } else {
+                r.a[0] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t0 * frame_sz + off));
+                r.b[0] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t1 * frame_sz + off));
+            }
+            return r;
+        };
+        auto unpack = [&](const RawPair &r, int (&e)[VEC], int (&o)[VEC]) {
+#pragma unroll
+            for (int i = 0; i < VEC / 2; i++) {
+                e[2 * i] = (int16_t)(r.a[i] & 0xffff); e[2 * i + 1] = (int)r.a[i] >> 16;
+                o[2 * i] = (int16_t)(r.b[i] & 0xffff); o[2 * i + 1] = (int)r.b[i] >> 16;
+            }
+        };
+        if (PF != 0 && ALICE_T_ROLLED) {
+            // Compile-time depth: a short unrolled prologue (warm-up and the mirrored left edge), a ROLLED
+            // steady-state loop with the rows of the next two pairs in flight, and three peeled pairs at the end
+            // (the last load is the only one that may need the frame clamp).  The fully unrolled form of this loop
+            // was 122 KB of code, four times the 32 KB instruction cache, and the warps of a block sit at different
+            // places in it: ncu showed as many no-instruction stalls as scoreboard stalls.
+            static_assert(PF == 0 || PF / 2 >= NST + 5, "compile-time depth too short for the pipelined form");
+            const int16_t *pn = src + off;                      // even row of the next pair to load
+            const size_t fs2 = 2 * frame_sz;
+            auto load_next = [&]() {                            // pair rows (pn, pn + frame_sz), no clamp
+                RawPair r;
+                if (VEC == 4) {
+                    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(pn));
+                    const uint2 b = __ldg(reinterpret_cast<const uint2 *>(pn + frame_sz));
+                    r.a[0] = a.x; r.a[VEC / 2 - 1] = a.y;
+                    r.b[0] = b.x; r.b[VEC / 2 - 1] = b.y;
+                } else {
+                    r.a[0] = __ldg(reinterpret_cast<const uint32_t *>(pn));
+                    r.b[0] = __ldg(reinterpret_cast<const uint32_t *>(pn + frame_sz));
+                }
+                pn += fs2;
+                return r;
+            };
+            RawPair r0 = load_next(), r1 = load_next(), r2 = r1;
+            auto steady = [&](int j) {                          // consumes r0 = pair j, emits pair j - NST
+                int e[VEC], o[VEC], lo[VEC], hi[VEC];
+                unpack(r0, e, o);
+#pragma unroll
+                for (int i = 0; i < VEC; i++) L[i].push_steady(e[i], o[i], lo[i], hi[i]);
+                emit(off, j - NST, lo, hi);
+                r0 = r1; r1 = r2;
+            };
+#pragma unroll
+            for (int j = 0; j <= NST; j++) {
+                r2 = load_next();                               // pair j + 2 <= NST + 2 < halft - 1
+                int e[VEC], o[VEC], lo[VEC], hi[VEC];
+                unpack(r0, e, o);
+                bool has = false;
+#pragma unroll
+                for (int i = 0; i < VEC; i++) has = L[i].push(e[i], o[i], j, j, lo[i], hi[i]);
+                if (has) emit(off, j - NST, lo, hi);
+                r0 = r1; r1 = r2;
+            }
+#pragma unroll 1
+            for (int j = NST + 1; j < halft - 3; j++) {
+                r2 = load_next();                               // pair j + 2 <= halft - 2
+                steady(j);
+            }
+            r2 = load_pair(halft - 1);                          // the last pair: its odd row may be frame f - 1 again
+            steady(halft - 3);
+            steady(halft - 2);
+            steady(halft - 1);
+            k = halft;
+        } else
 #pragma unroll
         for (int j = 0; j < halft; j++, k++) {
-            const int t0 = min(2 * j, f - 1), t1 = min(2 * j + 1, f - 1);  // pipeline.rs:107-112
             int e[VEC], o[VEC];
-            if (VEC == 4) {
-                uint2 a = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t0 * frame_sz + off));
-                uint2 b = __ldg(reinterpret_cast<const uint2 *>(src + (size_t)t1 * frame_sz + off));
-                e[0] = (int16_t)(a.x & 0xffff); e[1] = (int)a.x >> 16;
-                o[0] = (int16_t)(b.x & 0xffff); o[1] = (int)b.x >> 16;
-                if (VEC > 2) {
-                    e[VEC - 2] = (int16_t)(a.y & 0xffff); e[VEC - 1] = (int)a.y >> 16;
-                    o[VEC - 2] = (int16_t)(b.y & 0xffff); o[VEC - 1] = (int)b.y >> 16;
-                }
-            } else {
-                uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t0 * frame_sz + off));
-                uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)t1 * frame_sz + off));
-                e[0] = (int16_t)(a & 0xffff); e[1] = (int)a >> 16;
-                o[0] = (int16_t)(b & 0xffff); o[1] = (int)b >> 16;
-            }
+            unpack(load_pair(j), e, o);
             int lo[VEC], hi[VEC];
             bool has = false;
 #pragma unroll

@@ -71,6 +71,10 @@ SIGNATURES = {
     "alice_codec_build_histogram": (cint, [u8p, u64, u32p]),
     "alice_codec_rdo_bpp_from_quality": (dbl, [u8]),
     "alice_codec_rdo_compute_quantizer": (cint, [dbl, i32p, u64, u8, i32p, i32p]),
+    "alice_codec_rdo_estimate_variance": (cint, [i32p, u64, C.POINTER(C.c_double)]),
+    "alice_codec_rdo_compute_all_quantizers": (cint, [dbl, i32p, u32, u32, u32, i32p, i32p]),
+    "alice_codec_rdo_quantize_volume": (cint, [dbl, i32p, u32, u32, u32, i32p, u64, i32p, i32p]),
+    "alice_codec_psnr_device": (cint, [C.c_void_p, C.c_void_p, u64, C.c_void_p, C.POINTER(C.c_double)]),
     "alice_codec_freq_table_from_histogram": (cint, [u32p, u32, u16p, u16p, u8p]),
     "alice_codec_rans_encode": (cint, [u8p, u64, u32p, u32, C.POINTER(vp), u64p]),
     "alice_codec_rans_decode": (cint, [u8p, u64, u32p, u32, u8p, u64]),

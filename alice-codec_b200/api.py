@@ -201,6 +201,39 @@ class Api:
         self._chk(self.lib.alice_codec_rdo_compute_quantizer(target_bpp, pa, a.size, sb, C.byref(s), C.byref(d)))
         return s.value, d.value
 
+    def rdo_estimate_variance(self, coeffs) -> float:
+        a, pa = _i32(coeffs)
+        v = C.c_double()
+        self._chk(self.lib.alice_codec_rdo_estimate_variance(pa, a.size, C.byref(v)))
+        return v.value
+
+    def rdo_compute_all_quantizers(self, target_bpp, volume, width, height, depth):
+        """AnalyticalRDO::compute_all_quantizers on the 8 octants of a forward-transformed volume:
+        returns [(step, dead_zone)] * 8 indexed by the SubBand3D byte."""
+        a, pa = _i32(volume)
+        assert a.size == width * height * depth
+        s, d = np.zeros(8, np.int32), np.zeros(8, np.int32)
+        self._chk(self.lib.alice_codec_rdo_compute_all_quantizers(target_bpp, pa, width, height, depth,
+                                                                  s.ctypes.data_as(_capi.i32p), d.ctypes.data_as(_capi.i32p)))
+        return list(zip(s.tolist(), d.tolist()))
+
+    def rdo_quantize_volume(self, target_bpp, volume, width, height, depth):
+        """statistics -> quantisers -> FastQuantizer per octant; returns (quantised i32 volume, [(step, dz)] * 8)."""
+        a, pa = _i32(volume)
+        assert a.size == width * height * depth
+        out = np.empty(a.size, np.int32)
+        s, d = np.zeros(8, np.int32), np.zeros(8, np.int32)
+        self._chk(self.lib.alice_codec_rdo_quantize_volume(target_bpp, pa, width, height, depth,
+                                                           out.ctypes.data_as(_capi.i32p), out.size,
+                                                           s.ctypes.data_as(_capi.i32p), d.ctypes.data_as(_capi.i32p)))
+        return out, list(zip(s.tolist(), d.tolist()))
+
+    def psnr_device(self, d_a: int, d_b: int, n: int, stream: int = 0) -> float:
+        """alice_codec_psnr for two device buffers (raw device pointers)."""
+        v = C.c_double()
+        self._chk(self.lib.alice_codec_psnr_device(C.c_void_p(d_a), C.c_void_p(d_b), n, C.c_void_p(stream), C.byref(v)))
+        return v.value
+
     # ---- rANS (rans.rs)
     def freq_table_from_histogram(self, hist):
         h = np.ascontiguousarray(hist, dtype=np.uint32).reshape(-1)

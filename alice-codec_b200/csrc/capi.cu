@@ -455,37 +455,14 @@ double alice_codec_rdo_bpp_from_quality(uint8_t quality) {
     double q = (double)quality * RCP_100;
     return fma(q * q, 23.9, 0.1);
 }
-int alice_codec_rdo_compute_quantizer(double target_bpp, const int32_t *coeffs, uint64_t n64, uint8_t subband,
-                                      int32_t *step, int32_t *dead_zone) {
-    set_error(0, "");
-    if (subband > 7 || !step || !dead_zone) { set_error(kErrNull, "bad subband or null output"); return kErrNull; }
-    const size_t n = (size_t)n64;
-    double variance = 1.0;  // quant.rs:416-418
-    if (n > 0) {
-        if (!coeffs) { set_error(kErrNull, "null argument"); return kErrNull; }
-        if (!cuda_ready()) return kErrCuda;
-        DevBuf a, s, v;
-        if (!a.alloc(n * 4) || !s.alloc(8) || !v.alloc(8)) return kErrCuda;
-        CU_CHECK_RC(cudaMemcpy(a.p, coeffs, n * 4, cudaMemcpyHostToDevice));
-        CU_CHECK_RC(cudaMemset(s.p, 0, 8));
-        sum_i64(a.as<int32_t>(), n, s.as<long long>(), nullptr);
-        long long sum = 0;
-        CU_CHECK_RC(cudaMemcpy(&sum, s.p, 8, cudaMemcpyDeviceToHost));
-        const double inv_n = 1.0 / (double)n;
-        const double mean = (double)sum * inv_n;
-        variance_seq_f64(a.as<int32_t>(), n, mean, v.as<double>(), nullptr);
-        CU_CHECK_RC(cudaGetLastError());
-        double acc = 0;
-        CU_CHECK_RC(cudaMemcpy(&acc, v.p, 8, cudaMemcpyDeviceToHost));
-        variance = acc * inv_n;
-        if (!(variance > 1.0)) variance = 1.0;  // f64::max(1.0)
-    }
-    // quant.rs:440-468 — closed form on two scalars
+namespace {
+// quant.rs:440-468 — closed form on two scalars: lambda, base step, sub-band strength, dead zone
+void rdo_step_from_variance(double target_bpp, double variance, int subband, int32_t *step, int32_t *dead_zone) {
     const double ln2 = 0.693147180559945309417232121458176568;
     const double lambda = (6.0 * ln2 * variance) / target_bpp;
     const double r = round(sqrt(12.0 * lambda));
     int32_t base;
-    if (r != r) base = 0;
+    if (r != r) base = 0;                               // `as i32` saturates, NaN -> 0
     else if (r >= 2147483647.0) base = INT32_MAX;
     else if (r <= -2147483648.0) base = INT32_MIN;
     else base = (int32_t)r;
@@ -495,6 +472,151 @@ int alice_codec_rdo_compute_quantizer(double target_bpp, const int32_t *coeffs, 
     if (st < 1) st = 1;
     *step = st;
     *dead_zone = (int32_t)((uint32_t)st + (uint32_t)(st / 2));
+}
+// quant.rs:415-435 for up to 8 device-resident views; variance[i] = max(acc / n, 1.0), 1.0 for an empty view
+int rdo_variances(const RdoViewHost *views, int n_views, double *variance) {
+    double acc[8], mean[8];
+    cudaError_t e = rdo_seq_sums(views, n_views, acc, mean, nullptr);
+    if (e != cudaSuccess) { set_error(kErrCuda, cudaGetErrorString(e)); return kErrCuda; }
+    for (int i = 0; i < n_views; i++) {
+        double v = 1.0;
+        if (views[i].n > 0) {
+            const double inv_n = 1.0 / (double)views[i].n;
+            v = acc[i] * inv_n;
+            if (!(v > 1.0)) v = 1.0;                    // f64::max(1.0)
+        }
+        variance[i] = v;
+    }
+    return kOk;
+}
+// the 8 octants of a w x h x d volume (lib.rs:115-132: letters are x, y, t; index 4*[x high] + 2*[y high] + [t high]);
+// along each axis low = [0, dim/2), high = [dim/2, 2*(dim/2)) (an odd last sample belongs to no sub-band, wavelet.rs:220-233)
+void octant_views(const int32_t *d_vol, uint32_t w, uint32_t h, uint32_t d, RdoViewHost v[8]) {
+    const uint32_t hx = w / 2, hy = h / 2, ht = d / 2;
+    for (int sb = 0; sb < 8; sb++) {
+        const uint32_t x0 = (sb & 4) ? hx : 0, y0 = (sb & 2) ? hy : 0, t0 = (sb & 1) ? ht : 0;
+        v[sb].base = d_vol + ((size_t)t0 * h + y0) * w + x0;
+        v[sb].n = (unsigned long long)hx * hy * ht;
+        v[sb].sw = hx ? hx : 1;
+        v[sb].sh = hy ? hy : 1;
+        v[sb].row = w;
+        v[sb].plane = (unsigned long long)w * h;
+    }
+}
+bool fastq_constants(int32_t step, unsigned long long *recip, unsigned *shift) {
+    if (step <= 0) return false;                        // FastQuantizer::new (quant.rs:190-217)
+    const uint32_t su = (uint32_t)step;
+    const uint32_t extra = 32 - (uint32_t)__builtin_clz(su);
+    *shift = 32 + extra;
+    const unsigned __int128 power = (unsigned __int128)1 << *shift;
+    *recip = (unsigned long long)((power + su - 1) / su);
+    return true;
+}
+}  // namespace
+
+int alice_codec_rdo_compute_quantizer(double target_bpp, const int32_t *coeffs, uint64_t n64, uint8_t subband,
+                                      int32_t *step, int32_t *dead_zone) {
+    set_error(0, "");
+    if (subband > 7 || !step || !dead_zone) { set_error(kErrNull, "bad subband or null output"); return kErrNull; }
+    const size_t n = (size_t)n64;
+    double variance = 1.0;  // quant.rs:416-418
+    if (n > 0) {
+        if (!coeffs) { set_error(kErrNull, "null argument"); return kErrNull; }
+        if (!cuda_ready()) return kErrCuda;
+        DevBuf a;
+        if (!a.alloc(n * 4)) return kErrCuda;
+        CU_CHECK_RC(cudaMemcpy(a.p, coeffs, n * 4, cudaMemcpyHostToDevice));
+        RdoViewHost v;
+        v.base = a.as<int32_t>(); v.n = n; v.sw = 1u << 20; v.sh = 1u << 20;   // a flat slice: rows of 2^20 elements
+        v.row = v.sw; v.plane = (unsigned long long)v.sw * v.sh;
+        int rc = rdo_variances(&v, 1, &variance);
+        if (rc != kOk) return rc;
+    }
+    rdo_step_from_variance(target_bpp, variance, subband, step, dead_zone);
+    return kOk;
+}
+
+// AnalyticalRDO::estimate_variance (quant.rs:415-435; private in the reference, exported for the parity tests)
+int alice_codec_rdo_estimate_variance(const int32_t *coeffs, uint64_t n64, double *variance_out) {
+    set_error(0, "");
+    if (!variance_out) { set_error(kErrNull, "null output"); return kErrNull; }
+    const size_t n = (size_t)n64;
+    *variance_out = 1.0;
+    if (n == 0) return kOk;
+    if (!coeffs) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    DevBuf a;
+    if (!a.alloc(n * 4)) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpy(a.p, coeffs, n * 4, cudaMemcpyHostToDevice));
+    RdoViewHost v;
+    v.base = a.as<int32_t>(); v.n = n; v.sw = 1u << 20; v.sh = 1u << 20;
+    v.row = v.sw; v.plane = (unsigned long long)v.sw * v.sh;
+    return rdo_variances(&v, 1, variance_out);
+}
+
+// AnalyticalRDO::compute_all_quantizers (quant.rs:472-490) on the octants of a forward-transformed volume, each
+// octant gathered in row-major (t, y, x) order; steps8 / dead_zones8 are indexed by the SubBand3D byte.
+int alice_codec_rdo_compute_all_quantizers(double target_bpp, const int32_t *volume, uint32_t w, uint32_t h, uint32_t d,
+                                           int32_t *steps8, int32_t *dead_zones8) {
+    set_error(0, "");
+    if (!steps8 || !dead_zones8) { set_error(kErrNull, "null output"); return kErrNull; }
+    const unsigned __int128 tot = (unsigned __int128)w * h * d;
+    if (tot > ((unsigned __int128)1 << 40)) { set_error(kErrOverflow, "dimension overflow"); return kErrOverflow; }
+    const size_t n = (size_t)tot;
+    double variance[8];
+    for (int i = 0; i < 8; i++) variance[i] = 1.0;
+    if (n > 0) {
+        if (!volume) { set_error(kErrNull, "null argument"); return kErrNull; }
+        if (!cuda_ready()) return kErrCuda;
+        DevBuf a;
+        if (!a.alloc(n * 4)) return kErrCuda;
+        CU_CHECK_RC(cudaMemcpy(a.p, volume, n * 4, cudaMemcpyHostToDevice));
+        RdoViewHost v[8];
+        octant_views(a.as<int32_t>(), w, h, d, v);
+        int rc = rdo_variances(v, 8, variance);
+        if (rc != kOk) return rc;
+    }
+    for (int sb = 0; sb < 8; sb++) rdo_step_from_variance(target_bpp, variance[sb], sb, &steps8[sb], &dead_zones8[sb]);
+    return kOk;
+}
+
+// statistics -> quantisers -> FastQuantizer::quantize_buffer per octant (README.md:143-147 "manual pipeline", applied
+// per sub-band): out[i] = FastQuantizer::from(quantizers[octant(i)]).quantize(volume[i]).  The volume stays on the device
+// between the statistics and the quantiser pass.
+int alice_codec_rdo_quantize_volume(double target_bpp, const int32_t *volume, uint32_t w, uint32_t h, uint32_t d,
+                                    int32_t *out, uint64_t out_len, int32_t *steps8, int32_t *dead_zones8) {
+    set_error(0, "");
+    if (!steps8 || !dead_zones8) { set_error(kErrNull, "null output"); return kErrNull; }
+    const unsigned __int128 tot = (unsigned __int128)w * h * d;
+    if (tot > ((unsigned __int128)1 << 40)) { set_error(kErrOverflow, "dimension overflow"); return kErrOverflow; }
+    const size_t n = (size_t)tot;
+    if (out_len < n) { set_error(kErrBufferSize, "output smaller than input"); return kErrBufferSize; }
+    double variance[8];
+    for (int i = 0; i < 8; i++) variance[i] = 1.0;
+    DevBuf a, b;
+    if (n > 0) {
+        if (!volume || !out) { set_error(kErrNull, "null argument"); return kErrNull; }
+        if (!cuda_ready()) return kErrCuda;
+        if (!a.alloc(n * 4) || !b.alloc(n * 4)) return kErrCuda;
+        CU_CHECK_RC(cudaMemcpy(a.p, volume, n * 4, cudaMemcpyHostToDevice));
+        RdoViewHost v[8];
+        octant_views(a.as<int32_t>(), w, h, d, v);
+        int rc = rdo_variances(v, 8, variance);
+        if (rc != kOk) return rc;
+    }
+    int dz[8];
+    unsigned long long recip[8];
+    unsigned shift[8];
+    for (int sb = 0; sb < 8; sb++) {
+        rdo_step_from_variance(target_bpp, variance[sb], sb, &steps8[sb], &dead_zones8[sb]);
+        dz[sb] = dead_zones8[sb];
+        fastq_constants(steps8[sb], &recip[sb], &shift[sb]);    // steps are >= 1 by construction
+    }
+    if (n > 0) {
+        rdo_quantize_volume(a.as<int32_t>(), b.as<int32_t>(), w, h, d, dz, recip, shift, nullptr);
+        CU_CHECK_RC(cudaGetLastError());
+        CU_CHECK_RC(cudaMemcpy(out, b.p, n * 4, cudaMemcpyDeviceToHost));
+    }
     return kOk;
 }
 
@@ -714,6 +836,27 @@ int alice_codec_synth_rgb_device(int kind, uint32_t seed, uint32_t w, uint32_t h
     if (!cuda_ready()) return kErrCuda;
     synth_rgb(kind, seed, (int)w, (int)h, (int)f, d_rgb, (cudaStream_t)cuda_stream);
     CU_CHECK_RC(cudaGetLastError());
+    return kOk;
+}
+// alice_codec_psnr (ffi.rs:270, metrics.rs:16-63) for two device buffers: the squared differences are summed exactly
+// on the device (integers, total < 2^53, so equal to the reference's sequential f64 sum), the closed form runs here.
+int alice_codec_psnr_device(const uint8_t *d_a, const uint8_t *d_b, uint64_t len, void *cuda_stream, double *psnr_out) {
+    set_error(0, "");
+    if (!psnr_out) { set_error(kErrNull, "null output"); return kErrNull; }
+    if (len == 0) { *psnr_out = INFINITY; return kOk; }
+    if (!d_a || !d_b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (!cuda_ready()) return kErrCuda;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevBuf acc;
+    if (!acc.alloc(8)) return kErrCuda;
+    CU_CHECK_RC(cudaMemsetAsync(acc.p, 0, 8, st));
+    sq_diff_sum_u8(d_a, d_b, (size_t)len, acc.as<unsigned long long>(), st);
+    CU_CHECK_RC(cudaGetLastError());
+    unsigned long long sum = 0;
+    CU_CHECK_RC(cudaMemcpyAsync(&sum, acc.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK_RC(cudaStreamSynchronize(st));
+    const double mse = (double)sum / (double)len;
+    *psnr_out = mse == 0.0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / mse);
     return kOk;
 }
 void *alice_codec_pinned_alloc(uint64_t bytes) {

@@ -222,6 +222,39 @@ __global__ void k_variance_seq(const int32_t *__restrict__ in, size_t n, double 
     *acc_out = acc;
 }
 
+// metrics.rs:16-50 — sum of squared byte differences; every term is an integer <= 65025 and the total stays below
+// 2^53, so the exact integer sum equals the reference's sequential f64 sum bit for bit
+__global__ void k_sq_diff_sum(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t n,
+                              unsigned long long *sum) {
+    unsigned long long acc = 0;
+    const size_t nth = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n16 = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0 ? n / 16 : 0;
+    for (size_t i = tid; i < n16; i += nth) {
+        const uint4 va = reinterpret_cast<const uint4 *>(a)[i], vb = reinterpret_cast<const uint4 *>(b)[i];
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+        unsigned part = 0;                                  // 16 * 65025 fits easily
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int d = (int)((wa[k] >> (8 * j)) & 0xff) - (int)((wb[k] >> (8 * j)) & 0xff);
+                part += (unsigned)(d * d);
+            }
+        acc += part;
+    }
+    for (size_t i = n16 * 16 + tid; i < n; i += nth) {
+        const int d = (int)a[i] - (int)b[i];
+        acc += (unsigned)(d * d);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum, acc);
+}
+void sq_diff_sum_u8(const uint8_t *d_a, const uint8_t *d_b, size_t n, unsigned long long *d_sum, cudaStream_t st) {
+    if (!n) return;
+    ALICE_LAUNCH(k_sq_diff_sum, dim3(grid_for((long long)((n + 15) / 16), 256)), dim3(256), 0, st, d_a, d_b, n, d_sum);
+}
+
 void quantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int step, int dz, int *d_panic, cudaStream_t st) {
     if (!n) return;
     ALICE_LAUNCH(k_quantize, dim3(grid_for((long long)n, 256)), dim3(256), 0, st, d_in, d_out, n, step, dz, d_panic);

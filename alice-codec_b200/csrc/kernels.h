@@ -73,7 +73,23 @@ void to_symbols_u8(const int32_t *d_in, uint8_t *d_out, size_t n, cudaStream_t s
 void from_symbols_i32(const uint8_t *d_in, int32_t *d_out, size_t n, cudaStream_t st);
 void histogram_u8(const uint8_t *d_in, size_t n, unsigned *d_hist256, cudaStream_t st);  // adds into d_hist256
 void sum_i64(const int32_t *d_in, size_t n, long long *d_sum, cudaStream_t st);          // adds into *d_sum
+void sq_diff_sum_u8(const uint8_t *d_a, const uint8_t *d_b, size_t n, unsigned long long *d_sum,
+                    cudaStream_t st);                                                      // adds into *d_sum
 void variance_seq_f64(const int32_t *d_in, size_t n, double mean, double *d_acc, cudaStream_t st);
+
+// ---- AnalyticalRDO statistics and per-octant quantiser (k_rdo.cu) -------------------------
+struct RdoViewHost {     // a sub-box of a w x h x d i32 volume on the device, visited in row-major order
+    const int32_t *base; // first element of the sub-box
+    unsigned long long n;
+    unsigned sw, sh;     // sub-box width and height
+    unsigned long long row, plane;   // volume strides W and W*H
+};
+// h_acc[i] = the f64 sum of squared deviations of view i accumulated in slice order exactly as quant.rs:425-432
+// does (bit-identical to the sequential loop), h_mean[i] = its mean.  At most 8 views.  Synchronises `st`.
+cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc, double *h_mean, cudaStream_t st);
+// FastQuantizer::quantize of every element with the constants of its octant (index 4*[x>=w/2] + 2*[y>=h/2] + [t>=d/2])
+void rdo_quantize_volume(const int32_t *d_in, int32_t *d_out, unsigned w, unsigned h, unsigned d, const int dz[8],
+                         const unsigned long long recip[8], const unsigned shift[8], cudaStream_t st);
 
 // ---- synthetic inputs (k_synth.cu) ---------------------------------
 void synth_rgb(int kind, uint32_t seed, int w, int h, int f, uint8_t *d_rgb, cudaStream_t st);

@@ -124,6 +124,20 @@ int alice_codec_build_histogram(const uint8_t *symbols, uint64_t n, uint32_t *hi
 double alice_codec_rdo_bpp_from_quality(uint8_t quality);
 int alice_codec_rdo_compute_quantizer(double target_bpp, const int32_t *coeffs, uint64_t n, uint8_t subband,
                                       int32_t *step, int32_t *dead_zone);
+/* AnalyticalRDO::estimate_variance (quant.rs:415-435; private in the reference): max(1.0, f64 sum of squared
+ * deviations accumulated in slice order / n), 1.0 for an empty slice */
+int alice_codec_rdo_estimate_variance(const int32_t *coeffs, uint64_t n, double *variance_out);
+/* AnalyticalRDO::compute_all_quantizers (quant.rs:472-490) over the 8 octants of a forward-transformed w x h x d
+ * volume (index t*h*w + y*w + x).  Octant = SubBand3D byte = 4*[x >= w/2] + 2*[y >= h/2] + [t >= d/2] (lib.rs:115-132);
+ * each octant is the slice a caller would gather in row-major (t, y, x) order.  The f64 variance sum of every
+ * octant is bit-identical to the reference's sequential loop (quant.rs:425-432). */
+int alice_codec_rdo_compute_all_quantizers(double target_bpp, const int32_t *volume, uint32_t width, uint32_t height,
+                                           uint32_t depth, int32_t *steps8, int32_t *dead_zones8);
+/* statistics -> quantisers -> FastQuantizer::quantize_buffer (quant.rs:272-299) with the constants of each
+ * element's octant, the volume staying on the device in between; also returns the 8 (step, dead_zone) pairs */
+int alice_codec_rdo_quantize_volume(double target_bpp, const int32_t *volume, uint32_t width, uint32_t height,
+                                    uint32_t depth, int32_t *out, uint64_t out_len, int32_t *steps8,
+                                    int32_t *dead_zones8);
 
 /* FrequencyTable::from_histogram / uniform (rans.rs:102,158); n_symbols in 1..=256; outputs sized 256/256/4096 */
 int alice_codec_freq_table_from_histogram(const uint32_t *hist, uint32_t n_symbols, uint16_t *cum256,
@@ -181,6 +195,9 @@ uint64_t alice_codec_batch_device_bytes(const AliceBatch *b);
 /* synthetic RGB volumes generated on the device: kind 0=G0, 1=G1, 2=G2 */
 int alice_codec_synth_rgb_device(int kind, uint32_t seed, uint32_t width, uint32_t height, uint32_t frames,
                                  uint8_t *d_rgb, void *cuda_stream);
+/* alice_codec_psnr (ffi.rs:270) for two DEVICE buffers, e.g. a chunk's RGB input and its decode output; the sum of
+ * squared differences is an exact integer sum on the device, so the result equals the host function's bit for bit */
+int alice_codec_psnr_device(const uint8_t *d_a, const uint8_t *d_b, uint64_t len, void *cuda_stream, double *psnr_out);
 /* pinned host memory helpers for the host-buffer batch API */
 void *alice_codec_pinned_alloc(uint64_t bytes);
 void alice_codec_pinned_free(void *p);

@@ -253,6 +253,7 @@ template <class T> inline T __ldg(const T *p) { return *p; }
 using std::max;
 using std::min;
 template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 inline unsigned atomicAdd(unsigned *p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
 template <class T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicMax(T *p, T v) { T o = *p; *p = o > v ? o : v; return o; }
@@ -262,7 +263,7 @@ template <class T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; 
 typedef int cudaError_t;
 typedef struct emul_stream_t *cudaStream_t;
 typedef struct emul_event { double t; } *cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorUnknown = 999 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventDefault = 0, cudaHostAllocDefault = 0 };
 inline const char *cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated CUDA error"; }

@@ -123,6 +123,60 @@ def check_rdo(api, rng):
                 assert api.rdo_compute_quantizer(bpp, x, sb) == O.rdo_compute_quantizer(bpp, x, sb), (n, sb, bpp)
 
 
+def _octants(vol, w, h, d):
+    """the 8 sub-band slices of a forward-transformed volume in SubBand3D order (x, y, t letters), row-major"""
+    v = np.asarray(vol).reshape(d, h, w)
+    hx, hy, ht = w // 2, h // 2, d // 2
+    out = []
+    for sb in range(8):
+        x0, y0, t0 = (hx if sb & 4 else 0), (hy if sb & 2 else 0), (ht if sb & 1 else 0)
+        out.append(np.ascontiguousarray(v[t0:t0 + ht, y0:y0 + hy, x0:x0 + hx]).reshape(-1))
+    return out
+
+
+def check_rdo_exact_variance(api, rng, sizes=(1, 2, 31, 1024, 1025, 5000, 40000)):
+    """AnalyticalRDO::estimate_variance (quant.rs:415-435): the f64 sum is order dependent; the device result must
+    equal the sequential loop bit for bit, across binade changes, exact ties and absorbed terms."""
+    cases = []
+    for n in sizes:
+        cases.append(rng.integers(-500, 500, n, dtype=np.int64))
+        cases.append(rng.integers(-(1 << 31), 1 << 31, n, dtype=np.int64))                 # full i32 range
+        cases.append(np.where(rng.random(n) < 0.97, 0, rng.integers(-40000, 40000, n)))    # sparse, leading zeros
+        cases.append(rng.integers(0, 2, n, dtype=np.int64) * 2 - 1)                        # +-1: mean ~ 0, many ties
+        x = rng.integers(-3, 4, n, dtype=np.int64)
+        x[n // 2:] *= 1 << 20                                                              # small terms absorbed later
+        cases.append(x)
+        t = np.empty(n + (n & 1), np.int64)
+        t[0::2], t[1::2] = 1 << 20, 1 - (1 << 20)                                          # mean 0.5: every term ends in .25,
+        cases.append(t)                                                                    # exact ties once ulp = 0.5
+        cases.append(np.full(n, 7))                                                        # variance 0 -> floor 1.0
+        cases.append(np.concatenate([np.full(n // 2, 1 << 30), np.zeros(n - n // 2, np.int64)]))
+    for x in cases:
+        x = np.asarray(x, dtype=np.int64).astype(np.int32)
+        got, want = api.rdo_estimate_variance(x), O.rdo_estimate_variance(x)
+        assert np.float64(got).tobytes() == np.float64(want).tobytes(), (x.size, got, want)
+
+
+def check_rdo_octants(api, rng, shapes=((8, 6, 4), (16, 10, 6), (9, 7, 5), (2, 2, 2), (32, 18, 64))):
+    for (w, h, d) in shapes:
+        vol = (rng.standard_normal(w * h * d) * rng.choice([3, 50, 3000], w * h * d)).astype(np.int32)
+        for bpp in (0.1, O.rdo_bpp_from_quality(75), 24.0):
+            want = [O.rdo_compute_quantizer(bpp, o, sb) for sb, o in enumerate(_octants(vol, w, h, d))]
+            assert api.rdo_compute_all_quantizers(bpp, vol, w, h, d) == want, (w, h, d, bpp)
+            q, quants = api.rdo_quantize_volume(bpp, vol, w, h, d)
+            assert quants == want
+            # FastQuantizer == Quantizer (quant.rs:1145-1150), so the oracle's plain quantiser is the check
+            v3 = vol.reshape(d, h, w)
+            ref = np.empty_like(v3)
+            hx, hy, ht = w // 2, h // 2, d // 2
+            for t in range(d):
+                for y in range(h):
+                    for xs, sbx in ((slice(0, hx), 0), (slice(hx, w), 4)):
+                        sb = sbx | (2 if y >= hy else 0) | (1 if t >= ht else 0)
+                        ref[t, y, xs] = O.fast_quantize_buffer(want[sb][0], want[sb][1], v3[t, y, xs])
+            assert np.array_equal(q.reshape(d, h, w), ref), (w, h, d, bpp)
+
+
 def check_colour(api, rng, n=5000):
     rgb = rng.integers(0, 256, 3 * n, dtype=np.int64).astype(np.uint8)
     rgb[:12] = [0, 0, 0, 255, 255, 255, 255, 0, 0, 0, 0, 255]

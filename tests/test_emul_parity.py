@@ -50,6 +50,25 @@ def test_stage_apis(api):
     parity.check_rdo(api, rng)
 
 
+def test_rdo_exact_sum_and_octants(api):
+    rng = np.random.default_rng(7)
+    parity.check_rdo_exact_variance(api, rng, sizes=(1, 2, 31, 1024, 1025, 5000))
+    parity.check_rdo_octants(api, rng, shapes=((8, 6, 4), (9, 7, 5), (2, 2, 2), (32, 18, 8)))
+
+
+def test_psnr_device_kernel(api):
+    """the emulator's device pointers are host pointers, so the squared-difference kernel can be driven from numpy"""
+    rng = np.random.default_rng(3)
+    for n in (1, 15, 16, 4097, 50001):
+        a = rng.integers(0, 256, n + 16, dtype=np.uint8)
+        b = rng.integers(0, 256, n + 16, dtype=np.uint8)
+        for off in (0, 1):
+            x, y = a[off:off + n], b[off:off + n]
+            assert api.psnr_device(x.ctypes.data, y.ctypes.data, n) == O.psnr(x, y) == api.psnr(x, y)
+        assert api.psnr_device(a.ctypes.data, a.ctypes.data, n) == float("inf")
+    assert api.psnr_device(0, 0, 0) == float("inf")
+
+
 def test_rans_api(api):
     parity.check_rans_api(api, np.random.default_rng(2), n=3000)
 

@@ -148,6 +148,38 @@ def test_stage_apis(api):
     parity.check_rdo(api, rng)
 
 
+def test_rdo_exact_sum_and_octants(api):
+    """AnalyticalRDO statistics with the sequential f64 sum reproduced bit for bit by the parallel
+    binade scan (csrc/k_rdo.cu), compute_all_quantizers on the octants of a volume and the per-octant FastQuantizer."""
+    rng = np.random.default_rng(7)
+    parity.check_rdo_exact_variance(api, rng, sizes=(1, 2, 31, 1024, 1025, 5000, 40000, 1 << 20))
+    parity.check_rdo_octants(api, rng)
+    # a real forward-transformed volume: Y plane of G1, CDF 9/7
+    w, h, d = 64, 36, 64
+    y = O.rgb_bytes_to_ycocg_r(O.generate(O.G1, w, h, d))[0].astype(np.int32)
+    vol = O.wavelet3d_forward(1, y, w, h, d)
+    bpp = O.rdo_bpp_from_quality(80)
+    want = [O.rdo_compute_quantizer(bpp, o, sb) for sb, o in enumerate(parity._octants(vol, w, h, d))]
+    assert api.rdo_compute_all_quantizers(bpp, vol, w, h, d) == want
+
+
+def test_psnr_device_equals_host(api):
+    """alice_codec_psnr (ffi.rs:270) computed on the device for decode validation."""
+    import torch
+    rng = np.random.default_rng(3)
+    for n in (1, 15, 16, 4097, 3 * 640 * 360 * 2):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, n), 0, 255).astype(np.uint8)
+        ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        got = api.psnr_device(ta.data_ptr(), tb.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        assert got == api.psnr(a, b) == O.psnr(a, b), n
+        assert api.psnr_device(ta.data_ptr(), ta.data_ptr(), n) == float("inf")
+        # misaligned views take the byte path
+        if n > 20:
+            got = api.psnr_device(ta.data_ptr() + 1, tb.data_ptr() + 3, n - 3)
+            assert got == O.psnr(a[1:n - 2], b[3:n])
+
+
 def test_lossless_config4_transform(api):
     """BASELINE config 4: LosslessEncoder::transform_2d / inverse_2d (lossless.rs:45-54) == Wavelet2D::cdf53 per
     frame of the Y/Co/Cg planes; symbols (step 1, wrapping), histogram, table, rANS round trip per stream."""

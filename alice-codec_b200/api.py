@@ -275,6 +275,38 @@ def default_api() -> Api:
     return _default_api
 
 
+# ---- module-level functions of the reference's Python module (python.rs:274-277, 496-583, 598-609)
+def version() -> str:
+    """python.rs:274: the crate version the library is ABI-compatible with."""
+    return default_api().version()
+
+
+def rgb_to_ycocg_r_numpy(rgb_bytes):
+    """python.rs:496-527: 1-D uint8 [R0,G0,B0, R1,...] -> (y, co, cg) 1-D int16 arrays."""
+    a = np.asarray(rgb_bytes)
+    if a.dtype != np.uint8 or a.ndim != 1:
+        raise TypeError("rgb_bytes must be a 1-D uint8 NumPy array")
+    if not a.flags.c_contiguous:
+        raise ValueError("rgb_bytes must be C-contiguous")
+    return default_api().rgb_to_ycocg_r(a)
+
+
+def ycocg_r_to_rgb_numpy(y, co, cg):
+    """python.rs:540-583: three 1-D int16 arrays of equal length -> 1-D uint8 interleaved RGB."""
+    arrs = []
+    for name, v in (("y", y), ("co", co), ("cg", cg)):
+        a = np.asarray(v)
+        if a.dtype != np.int16 or a.ndim != 1:
+            raise TypeError(f"{name} must be a 1-D int16 NumPy array")
+        arrs.append(a)
+    if not (arrs[0].size == arrs[1].size == arrs[2].size):
+        raise ValueError("y, co, cg arrays must have the same length")
+    for name, a in zip(("y", "co", "cg"), arrs):
+        if not a.flags.c_contiguous:
+            raise ValueError(f"{name} must be C-contiguous")
+    return default_api().ycocg_r_to_rgb(*arrs)
+
+
 class EncodedChunk:
     """python.rs:287-357 / pipeline.rs:172-313."""
 
@@ -332,8 +364,8 @@ class EncodedChunk:
         return EncodedChunk(h, api)
 
     def __repr__(self):
-        return (f"EncodedChunk({self.width}x{self.height}x{self.frames}, wavelet={self.wavelet}, "
-                f"compressed={self.compressed_size} bytes)")
+        # python.rs:343-355
+        return f"EncodedChunk({self.width}x{self.height}x{self.frames}, {self.compressed_size} bytes, {self.wavelet})"
 
 
 class FrameEncoder:

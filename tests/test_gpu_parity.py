@@ -180,6 +180,34 @@ def test_psnr_device_equals_host(api):
             assert got == O.psnr(a[1:n - 2], b[3:n])
 
 
+def test_python_module_surface():
+    """the names, defaults and error texts of the reference's Python module (src/python.rs:274-609) on top
+    of the C ABI: FrameEncoder / FrameDecoder / EncodedChunk, rgb_to_ycocg_r_numpy, ycocg_r_to_rgb_numpy, version."""
+    assert pkg.version() == "0.1.2"                                             # python.rs:274, Cargo.toml:3
+    rgb = O.generate(O.G1, 16, 8, 2)
+    y, co, cg = pkg.rgb_to_ycocg_r_numpy(rgb)
+    ry, rco, rcg = O.rgb_bytes_to_ycocg_r(rgb)
+    assert y.dtype == np.int16 and np.array_equal(y, ry) and np.array_equal(co, rco) and np.array_equal(cg, rcg)
+    assert np.array_equal(pkg.ycocg_r_to_rgb_numpy(y, co, cg), rgb)
+    with pytest.raises(ValueError, match="multiple of 3"):                       # python.rs:508-512
+        pkg.rgb_to_ycocg_r_numpy(rgb[:-1])
+    with pytest.raises(ValueError, match="same length"):                         # python.rs:551-555
+        pkg.ycocg_r_to_rgb_numpy(y, co[:-1], cg)
+    with pytest.raises(ValueError, match="C-contiguous"):                        # python.rs:505
+        pkg.rgb_to_ycocg_r_numpy(np.zeros(12, np.uint8)[::2])
+    with pytest.raises(ValueError, match="unknown wavelet type 'dwt'"):          # python.rs:385-389
+        pkg.FrameEncoder(wavelet="dwt")
+    enc = pkg.FrameEncoder()                                                     # quality=90, wavelet="cdf53" (python.rs:378)
+    chunk = enc.encode(rgb, 16, 8, 2)
+    assert chunk.to_bytes() == O.encode(rgb, 16, 8, 2, 90, O.CDF53)
+    assert (chunk.width, chunk.height, chunk.frames, chunk.wavelet) == (16, 8, 2, "cdf53")
+    assert repr(chunk) == f"EncodedChunk(16x8x2, {chunk.compressed_size} bytes, cdf53)"   # python.rs:343-355
+    back = pkg.EncodedChunk.from_bytes(chunk.to_bytes())
+    assert np.array_equal(pkg.FrameDecoder().decode(back), O.decode(chunk.to_bytes()))
+    with pytest.raises(ValueError):                                              # CodecError -> ValueError (python.rs:61-63)
+        enc.encode(rgb[:-3], 16, 8, 2)
+
+
 def test_lossless_config4_transform(api):
     """BASELINE config 4: LosslessEncoder::transform_2d / inverse_2d (lossless.rs:45-54) == Wavelet2D::cdf53 per
     frame of the Y/Co/Cg planes; symbols (step 1, wrapping), histogram, table, rANS round trip per stream."""

@@ -77,7 +77,9 @@ SIGNATURES = {
     "alice_codec_psnr_device": (cint, [C.c_void_p, C.c_void_p, u64, C.c_void_p, C.POINTER(C.c_double)]),
     "alice_codec_freq_table_from_histogram": (cint, [u32p, u32, u16p, u16p, u8p]),
     "alice_codec_rans_encode": (cint, [u8p, u64, u32p, u32, C.POINTER(vp), u64p]),
+    "alice_codec_rans_encode_interleaved": (cint, [u8p, u64, u32p, u32, C.POINTER(vp), u64p]),
     "alice_codec_rans_decode": (cint, [u8p, u64, u32p, u32, u8p, u64]),
+    "alice_codec_rans_decode_interleaved": (cint, [u8p, u64, u32p, u32, u8p, u64]),
     "alice_codec_encode_stages": (vp, [vp, u8p, u64, u32, u32, u32, i32p, u8p]),
     "alice_codec_decode_stages": (vp, [vp, u64p, u8p]),
     "alice_codec_batch_create": (vp, [u8, u8, u32, u32, u32, u32, vp]),

@@ -259,6 +259,25 @@ class Api:
                                                    out.ctypes.data_as(_capi.u8p), n))
         return out
 
+    def rans_encode_interleaved(self, symbols, hist) -> bytes:
+        """InterleavedRansEncoder::encode + finish (rans.rs:393-459); not the .alc stream format."""
+        a, pa = _u8(symbols)
+        h = np.ascontiguousarray(hist, dtype=np.uint32).reshape(-1)
+        out, n = C.c_void_p(), C.c_uint64()
+        self._chk(self.lib.alice_codec_rans_encode_interleaved(pa, a.size, h.ctypes.data_as(_capi.u32p), h.size,
+                                                               C.byref(out), C.byref(n)))
+        return self._take(out, n.value)
+
+    def rans_decode_interleaved(self, stream: bytes, n: int, hist) -> np.ndarray:
+        """InterleavedRansDecoder::new + decode_n (rans.rs:465-524)."""
+        buf = np.frombuffer(bytes(stream), dtype=np.uint8)
+        h = np.ascontiguousarray(hist, dtype=np.uint32).reshape(-1)
+        out = np.empty(n, np.uint8)
+        self._chk(self.lib.alice_codec_rans_decode_interleaved(
+            buf.ctypes.data_as(_capi.u8p) if buf.size else None, buf.size, h.ctypes.data_as(_capi.u32p), h.size,
+            out.ctypes.data_as(_capi.u8p), n))
+        return out
+
     def psnr(self, a, b) -> float:
         (a, pa), (b, pb) = _u8(a), _u8(b)
         assert a.size == b.size

@@ -709,6 +709,136 @@ int alice_codec_rans_decode(const uint8_t *stream, uint64_t len64, const uint32_
     return kOk;
 }
 
+// InterleavedRansEncoder::{encode, finish} (rans.rs:393-459): four independent RansEncoder streams over symbols
+// i % 4 == k, run as four lanes of the one-warp-per-stream kernel; container = 4 lengths + 4 counts + the streams.
+int alice_codec_rans_encode_interleaved(const uint8_t *symbols, uint64_t n64, const uint32_t *hist, uint32_t n_symbols,
+                                        uint8_t **out, uint64_t *out_len) {
+    set_error(0, "");
+    if (!hist || !out || !out_len || (n64 && !symbols)) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (n_symbols == 0) { set_error(kErrPanic, "empty histogram"); return kErrPanic; }
+    if (n_symbols > 256) { set_error(kErrDimensions, "n_symbols > 256"); return kErrDimensions; }
+    const size_t n = (size_t)n64;
+    for (size_t i = 0; i < n; i++)
+        if (symbols[i] >= n_symbols) { set_error(kErrPanic, "symbol outside the table"); return kErrPanic; }
+    if (!cuda_ready()) return kErrCuda;
+    size_t count[4];
+    for (int k = 0; k < 4; k++) count[k] = (n + 3 - (size_t)k) / 4;             // rans.rs:421-423
+    const size_t stride = (count[0] + 15) / 16 * 16 + 16;
+    const size_t cap = rans_enc_worst_case(count[0]);
+    DevBuf h, enc, dec, aux, sy, pl, pay, job, res;
+    if (!h.alloc(4 * 1024) || !enc.alloc(4 * kEncTableBytes) || !dec.alloc(4 * kDecLutEntries * 4) ||
+        !aux.alloc(4 * sizeof(DecAux)) || !sy.alloc(n) || !pl.alloc(4 * stride) || !pay.alloc(4 * cap) ||
+        !job.alloc(4 * sizeof(RansEncJob)) || !res.alloc(4 * 16))
+        return kErrCuda;
+    CU_CHECK_RC(cudaMemset(h.p, 0, 4 * 1024));
+    for (int k = 0; k < 4; k++)
+        CU_CHECK_RC(cudaMemcpy(h.as<uint8_t>() + 1024 * k, hist, n_symbols * 4, cudaMemcpyHostToDevice));
+    if (n) CU_CHECK_RC(cudaMemcpy(sy.p, symbols, n, cudaMemcpyHostToDevice));
+    deinterleave4_u8(sy.as<uint8_t>(), n, pl.as<uint8_t>(), stride, nullptr);
+    build_tables(h.as<unsigned>(), 4, (int)n_symbols, enc.as<EncSym>(), dec.as<uint32_t>(), aux.as<DecAux>(), nullptr,
+                 nullptr, nullptr, nullptr);
+    RansEncJob j[4];
+    for (int k = 0; k < 4; k++) {
+        j[k].symbols = pl.as<uint8_t>() + k * stride; j[k].n = count[k];
+        j[k].out = pay.as<uint8_t>() + k * cap; j[k].cap = cap;
+    }
+    CU_CHECK_RC(cudaMemcpy(job.p, j, sizeof(j), cudaMemcpyHostToDevice));
+    rans_encode(job.as<RansEncJob>(), enc.as<EncSym>(), nullptr, res.as<unsigned long long>(), 4, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    unsigned long long r[8];
+    CU_CHECK_RC(cudaMemcpy(r, res.p, sizeof(r), cudaMemcpyDeviceToHost));
+    size_t total = 32;
+    for (int k = 0; k < 4; k++) {
+        if (r[2 * k + 1] & 2) { set_error(kErrPanic, "symbol with zero frequency in use: the reference aborts"); return kErrPanic; }
+        if (r[2 * k + 1]) { set_error(kErrCuda, "rANS output overflow"); return kErrCuda; }
+        total += (size_t)r[2 * k];
+    }
+    uint8_t *p = (uint8_t *)malloc(total);
+    if (!p) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
+    size_t o = 32;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t len = (uint32_t)r[2 * k], cnt = (uint32_t)count[k];     // `as u32` (rans.rs:443, 449)
+        memcpy(p + 4 * k, &len, 4);
+        memcpy(p + 16 + 4 * k, &cnt, 4);
+        if (cudaMemcpy(p + o, pay.as<uint8_t>() + k * cap + cap - r[2 * k], (size_t)r[2 * k], cudaMemcpyDeviceToHost) != cudaSuccess) {
+            free(p);
+            set_error(kErrCuda, "copy failed");
+            return kErrCuda;
+        }
+        o += (size_t)r[2 * k];
+    }
+    *out = p;
+    *out_len = total;
+    return kOk;
+}
+
+// InterleavedRansDecoder::{new, decode_n} (rans.rs:465-524).  Slices past the input (the reference panics) and
+// n larger than the four symbol counts (the reference spins forever, rans.rs:511-513) return ALICE_ERR_PANIC.
+int alice_codec_rans_decode_interleaved(const uint8_t *stream, uint64_t len64, const uint32_t *hist, uint32_t n_symbols,
+                                        uint8_t *symbols_out, uint64_t n64) {
+    set_error(0, "");
+    if (!hist || (n64 && !symbols_out) || (len64 && !stream)) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (n_symbols == 0) { set_error(kErrPanic, "empty histogram"); return kErrPanic; }
+    if (n_symbols > 256) { set_error(kErrDimensions, "n_symbols > 256"); return kErrDimensions; }
+    const size_t n = (size_t)n64, len = (size_t)len64;
+    if (len < 32) { set_error(kErrPanic, "container shorter than its 32-byte header: the reference panics"); return kErrPanic; }
+    size_t slen[4], start[4];
+    unsigned long long cnt[4], total = 0;
+    size_t o = 32;
+    for (int k = 0; k < 4; k++) {
+        uint32_t l, c;
+        memcpy(&l, stream + 4 * k, 4);
+        memcpy(&c, stream + 16 + 4 * k, 4);
+        slen[k] = l; cnt[k] = c; total += c; start[k] = o;
+        o += l;
+        if (o > len) { set_error(kErrPanic, "stream lengths exceed the container: the reference panics"); return kErrPanic; }
+    }
+    if (n > total) { set_error(kErrPanic, "more symbols requested than the streams hold: the reference never returns"); return kErrPanic; }
+    if (n == 0) return kOk;
+    if (!cuda_ready()) return kErrCuda;
+    // symbols each stream contributes to the first n outputs: rounds are complete up to r, then a partial round
+    unsigned long long need[4] = {0, 0, 0, 0};
+    {
+        unsigned long long left = n, r = 0;
+        while (left) {
+            unsigned m = 0;
+            unsigned long long r_next = ~0ull;
+            for (int k = 0; k < 4; k++) if (cnt[k] > r) { m++; if (cnt[k] < r_next) r_next = cnt[k]; }
+            const unsigned long long full = (r_next - r) * m;
+            if (left >= full) { for (int k = 0; k < 4; k++) if (cnt[k] > r) need[k] = r_next; left -= full; r = r_next; continue; }
+            const unsigned long long q = left / m, rem = left % m;
+            unsigned seen = 0;
+            for (int k = 0; k < 4; k++) if (cnt[k] > r) { need[k] = r + q + (seen < rem ? 1 : 0); seen++; }
+            left = 0;
+        }
+    }
+    unsigned long long max_need = 0;
+    for (int k = 0; k < 4; k++) if (need[k] > max_need) max_need = need[k];
+    const size_t stride = ((size_t)max_need + 15) / 16 * 16 + 16;
+    DevBuf h, enc, dec, aux, pl, in, job, outb;
+    if (!h.alloc(4 * 1024) || !enc.alloc(4 * kEncTableBytes) || !dec.alloc(4 * kDecLutEntries * 4) ||
+        !aux.alloc(4 * sizeof(DecAux)) || !pl.alloc(4 * stride) || !in.alloc(len + 32) ||
+        !job.alloc(4 * sizeof(RansDecJob)) || !outb.alloc(n))
+        return kErrCuda;
+    CU_CHECK_RC(cudaMemset(h.p, 0, 4 * 1024));
+    for (int k = 0; k < 4; k++)
+        CU_CHECK_RC(cudaMemcpy(h.as<uint8_t>() + 1024 * k, hist, n_symbols * 4, cudaMemcpyHostToDevice));
+    CU_CHECK_RC(cudaMemcpy(in.p, stream, len, cudaMemcpyHostToDevice));
+    build_tables(h.as<unsigned>(), 4, (int)n_symbols, enc.as<EncSym>(), dec.as<uint32_t>(), aux.as<DecAux>(), nullptr,
+                 nullptr, nullptr, nullptr);
+    RansDecJob j[4];
+    for (int k = 0; k < 4; k++) {
+        j[k].in = in.as<uint8_t>() + start[k]; j[k].len = slen[k];
+        j[k].symbols = pl.as<uint8_t>() + k * stride; j[k].n = need[k];
+    }
+    CU_CHECK_RC(cudaMemcpy(job.p, j, sizeof(j), cudaMemcpyHostToDevice));
+    rans_decode(job.as<RansDecJob>(), dec.as<uint32_t>(), aux.as<DecAux>(), 4, nullptr);
+    interleave_rr_u8(pl.as<uint8_t>(), stride, outb.as<uint8_t>(), n, cnt, nullptr);
+    CU_CHECK_RC(cudaGetLastError());
+    CU_CHECK_RC(cudaMemcpy(symbols_out, outb.p, n, cudaMemcpyDeviceToHost));
+    return kOk;
+}
+
 EncodedChunk *alice_codec_encode_stages(const FrameEncoder *enc, const uint8_t *rgb, uint64_t rgb_len, uint32_t w,
                                         uint32_t h, uint32_t f, int32_t *coeffs_out, uint8_t *symbols_out) {
     return encode_impl(enc, rgb, rgb_len, w, h, f, coeffs_out, symbols_out);

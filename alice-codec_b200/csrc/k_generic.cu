@@ -4,6 +4,8 @@
 // These follow the reference's i32-wrapping / i64-product arithmetic literally and favour
 // obviousness over speed; the .alc pipeline uses the fused kernels of k_forward.cu /
 // k_inverse.cu instead.
+#include <string.h>
+
 #include "kernels.h"
 #include "lifting.cuh"
 
@@ -253,6 +255,51 @@ __global__ void k_sq_diff_sum(const uint8_t *__restrict__ a, const uint8_t *__re
 void sq_diff_sum_u8(const uint8_t *d_a, const uint8_t *d_b, size_t n, unsigned long long *d_sum, cudaStream_t st) {
     if (!n) return;
     ALICE_LAUNCH(k_sq_diff_sum, dim3(grid_for((long long)((n + 15) / 16), 256)), dim3(256), 0, st, d_a, d_b, n, d_sum);
+}
+
+// rans.rs:420-430 — InterleavedRansEncoder: symbol i belongs to stream i % 4.  planes[k * stride + j] = in[4j + k].
+__global__ void k_deinterleave4(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ planes, size_t stride) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nth) planes[(i & 3) * stride + (i >> 2)] = in[i];
+}
+// rans.rs:508-520 — InterleavedRansDecoder::decode_n visits the streams round-robin and skips exhausted ones, so the
+// output is a sequence of segments in each of which a fixed set of `m` streams alternates: output o of segment s is
+// symbol r0 + (o - base) / m of stream act[(o - base) % m].
+struct RrSegments { unsigned long long base[5]; unsigned long long r0[4]; unsigned m[4]; unsigned act[4][4]; int n_seg; };
+__global__ void k_interleave_rr(const uint8_t *__restrict__ planes, size_t stride, uint8_t *__restrict__ out, size_t n,
+                                RrSegments sg) {
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += nth) {
+        int s = 0;
+        while (s + 1 < sg.n_seg && o >= sg.base[s + 1]) s++;
+        const unsigned long long local = o - sg.base[s];
+        const unsigned m = sg.m[s];
+        out[o] = planes[(size_t)sg.act[s][local % m] * stride + (size_t)(sg.r0[s] + local / m)];
+    }
+}
+void deinterleave4_u8(const uint8_t *d_in, size_t n, uint8_t *d_planes, size_t stride, cudaStream_t st) {
+    if (!n) return;
+    ALICE_LAUNCH(k_deinterleave4, dim3(grid_for((long long)n, 256)), dim3(256), 0, st, d_in, n, d_planes, stride);
+}
+void interleave_rr_u8(const uint8_t *d_planes, size_t stride, uint8_t *d_out, size_t n, const unsigned long long counts[4],
+                      cudaStream_t st) {
+    if (!n) return;
+    RrSegments sg;
+    memset(&sg, 0, sizeof(sg));
+    unsigned long long r = 0, base = 0;
+    while (sg.n_seg < 4) {                                   // rounds [r, r_next) in which the same streams are alive
+        unsigned m = 0;
+        unsigned long long r_next = ~0ull;
+        for (unsigned k = 0; k < 4; k++)
+            if (counts[k] > r) { sg.act[sg.n_seg][m++] = k; if (counts[k] < r_next) r_next = counts[k]; }
+        if (m == 0) break;
+        sg.base[sg.n_seg] = base; sg.r0[sg.n_seg] = r; sg.m[sg.n_seg] = m;
+        base += (r_next - r) * m;
+        r = r_next;
+        sg.n_seg++;
+    }
+    sg.base[sg.n_seg] = base;
+    ALICE_LAUNCH(k_interleave_rr, dim3(grid_for((long long)n, 256)), dim3(256), 0, st, d_planes, stride, d_out, n, sg);
 }
 
 void quantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int step, int dz, int *d_panic, cudaStream_t st) {

@@ -75,6 +75,10 @@ void histogram_u8(const uint8_t *d_in, size_t n, unsigned *d_hist256, cudaStream
 void sum_i64(const int32_t *d_in, size_t n, long long *d_sum, cudaStream_t st);          // adds into *d_sum
 void sq_diff_sum_u8(const uint8_t *d_a, const uint8_t *d_b, size_t n, unsigned long long *d_sum,
                     cudaStream_t st);                                                      // adds into *d_sum
+// InterleavedRansEncoder / Decoder symbol order (rans.rs:420-430, 508-520): planes[k * stride + j] <-> stream k, symbol j
+void deinterleave4_u8(const uint8_t *d_in, size_t n, uint8_t *d_planes, size_t stride, cudaStream_t st);
+void interleave_rr_u8(const uint8_t *d_planes, size_t stride, uint8_t *d_out, size_t n, const unsigned long long counts[4],
+                      cudaStream_t st);
 void variance_seq_f64(const int32_t *d_in, size_t n, double mean, double *d_acc, cudaStream_t st);
 
 // ---- AnalyticalRDO statistics and per-octant quantiser (k_rdo.cu) -------------------------

@@ -150,6 +150,15 @@ int alice_codec_rans_encode(const uint8_t *symbols, uint64_t n, const uint32_t *
 int alice_codec_rans_decode(const uint8_t *stream, uint64_t len, const uint32_t *hist, uint32_t n_symbols,
                             uint8_t *symbols_out, uint64_t n);
 
+/* InterleavedRansEncoder / InterleavedRansDecoder (rans.rs:393-524): the reference's 4-stream container (4 stream
+ * lengths + 4 symbol counts, u32 LE, then the streams; symbol i in stream i % 4).  Opt-in and NOT the .alc format:
+ * the only intra-channel entropy-coding parallelism the reference defines.  Same table rules and
+ * ownership as alice_codec_rans_encode / _decode. */
+int alice_codec_rans_encode_interleaved(const uint8_t *symbols, uint64_t n, const uint32_t *hist, uint32_t n_symbols,
+                                        uint8_t **out, uint64_t *out_len);
+int alice_codec_rans_decode_interleaved(const uint8_t *stream, uint64_t len, const uint32_t *hist, uint32_t n_symbols,
+                                        uint8_t *symbols_out, uint64_t n);
+
 /* stage dumps for parity tests: as alice_codec_encode / alice_codec_decode, additionally copying out the
  * wavelet coefficients before quantisation (i32 [3][N], only via the generic path when requested) and the
  * symbol planes (u8 [3][N]), N = padded pixels.  Any dump pointer may be null. */

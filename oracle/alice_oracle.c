@@ -574,6 +574,93 @@ int alo_rans_decode(const uint8_t *in, size_t len, size_t n, const alo_freq_tabl
     return ALO_OK;
 }
 
+/* rans.rs:393-459 InterleavedRansEncoder::{new, encode, finish}: symbol i goes to encoder i % 4, visited in
+ * reverse order; container = 4 stream lengths (u32 LE) + 4 symbol counts (u32 LE) + the four streams */
+int alo_rans_encode_interleaved(const uint8_t *symbols, size_t n, const alo_freq_table *t, uint8_t **out,
+                                size_t *out_len) {
+    uint32_t state[4] = {RANS32_L, RANS32_L, RANS32_L, RANS32_L};
+    bytevec v[4] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    size_t count[4];
+    int rc = ALO_OK;
+    for (int i = 0; i < 4; i++) count[i] = (n + 3 - (size_t)i) / 4;              /* rans.rs:421-423 */
+    for (size_t k = n; k-- > 0 && rc == ALO_OK;) {                               /* rans.rs:426-430 */
+        int st = (int)(k % 4);
+        uint8_t sym = symbols[k];
+        if (sym >= t->n_symbols) { rc = ALO_ERR_PANIC; break; }
+        uint32_t freq = t->freq[sym], cum_freq = t->cum[sym];
+        if (freq == 0) { rc = ALO_ERR_PANIC; break; }
+        uint64_t x_max = (((uint64_t)(RANS32_L >> PROB_BITS)) << 8) * (uint64_t)freq;
+        while ((uint64_t)state[st] >= x_max) {
+            if (bv_push(&v[st], (uint8_t)(state[st] & 0xFF))) { rc = ALO_ERR_PANIC; break; }
+            state[st] >>= 8;
+        }
+        uint32_t q = state[st] / freq, r = state[st] % freq;
+        state[st] = (q << PROB_BITS) + r + cum_freq;
+    }
+    size_t total = 32;
+    for (int i = 0; i < 4 && rc == ALO_OK; i++) {                                /* RansEncoder::finish, rans.rs:298-308 */
+        for (int b = 0; b < 4; b++) bv_push(&v[i], (uint8_t)((state[i] >> (8 * b)) & 0xFF));
+        for (size_t a = 0, z = v[i].len - 1; a < z; a++, z--) { uint8_t tmp = v[i].data[a]; v[i].data[a] = v[i].data[z]; v[i].data[z] = tmp; }
+        total += v[i].len;
+    }
+    uint8_t *res = rc == ALO_OK ? (uint8_t *)malloc(total) : NULL;
+    if (rc == ALO_OK && !res) rc = ALO_ERR_PANIC;
+    if (rc == ALO_OK) {
+        size_t o = 0;
+        for (int i = 0; i < 4; i++) { uint32_t l = (uint32_t)v[i].len; memcpy(res + o, &l, 4); o += 4; }      /* rans.rs:441-445 */
+        for (int i = 0; i < 4; i++) { uint32_t c = (uint32_t)count[i]; memcpy(res + o, &c, 4); o += 4; }      /* rans.rs:448-450 */
+        for (int i = 0; i < 4; i++) { memcpy(res + o, v[i].data, v[i].len); o += v[i].len; }                  /* rans.rs:453-455 */
+        *out = res;
+        *out_len = total;
+    }
+    for (int i = 0; i < 4; i++) free(v[i].data);
+    return rc;
+}
+
+/* rans.rs:465-524 InterleavedRansDecoder::{new, decode_n}.  Slicing past the input panics; asking for more symbols
+ * than the four counts hold spins forever in the reference (rans.rs:511-513) — both are reported as ALO_ERR_PANIC. */
+int alo_rans_decode_interleaved(const uint8_t *in, size_t len, size_t n, const alo_freq_table *t, uint8_t *out) {
+    if (len < 32) return ALO_ERR_PANIC;
+    size_t slen[4], remaining[4], start[4], pos[4];
+    uint32_t state[4];
+    size_t o = 32, total = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t l, c;
+        memcpy(&l, in + 4 * i, 4);
+        memcpy(&c, in + 16 + 4 * i, 4);
+        slen[i] = l; remaining[i] = c; total += c;
+        start[i] = o;
+        o += l;
+        if (o > len) return ALO_ERR_PANIC;
+    }
+    if (n > total) return ALO_ERR_PANIC;
+    for (int i = 0; i < 4; i++) {                                                /* RansDecoder::new on each slice */
+        const uint8_t *p = in + start[i];
+        state[i] = 0; pos[i] = 0;
+        if (slen[i] >= 4) {
+            state[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+            pos[i] = 4;
+        }
+    }
+    int idx = 0;
+    for (size_t k = 0; k < n; k++) {
+        while (remaining[idx] == 0) idx = (idx + 1) % 4;                         /* rans.rs:511-513 */
+        const uint8_t *p = in + start[idx];
+        uint32_t slot = state[idx] & (PROB_SCALE - 1);
+        uint8_t sym = t->lut[slot];
+        uint64_t freq = t->freq[sym], cum = t->cum[sym];
+        state[idx] = (uint32_t)(freq * (uint64_t)(state[idx] >> PROB_BITS) + (uint64_t)slot - cum);
+        while (state[idx] < RANS32_L && pos[idx] < slen[idx]) {
+            state[idx] = (state[idx] << 8) | (uint32_t)p[pos[idx]];
+            pos[idx]++;
+        }
+        out[k] = sym;
+        remaining[idx]--;
+        idx = (idx + 1) % 4;
+    }
+    return ALO_OK;
+}
+
 void alo_free(void *p) { free(p); }
 
 /* ---------------------------------------------------------------- pipeline */

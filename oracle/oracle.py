@@ -97,6 +97,8 @@ def lib():
         L.alo_freq_table_from_histogram.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(FreqTable)]
         L.alo_rans_encode.argtypes = [p8, sz, C.POINTER(FreqTable), C.POINTER(p8), C.POINTER(sz)]
         L.alo_rans_decode.argtypes = [p8, sz, sz, C.POINTER(FreqTable), p8]
+        L.alo_rans_encode_interleaved.argtypes = [p8, sz, C.POINTER(FreqTable), C.POINTER(p8), C.POINTER(sz)]
+        L.alo_rans_decode_interleaved.argtypes = [p8, sz, sz, C.POINTER(FreqTable), p8]
         L.alo_free.argtypes = [C.c_void_p]
         L.alo_free.restype = None
         L.alo_quality_to_step.argtypes = [C.c_uint8]
@@ -295,6 +297,26 @@ def rans_decode(stream: bytes, n: int, table: FreqTable) -> np.ndarray:
     buf = np.ascontiguousarray(buf)
     out = np.empty(n, np.uint8)
     _chk(lib().alo_rans_decode(_p8(buf) if buf.size else None, buf.size, n, C.byref(table), _p8(out)))
+    return out
+
+
+def rans_encode_interleaved(symbols, table: FreqTable) -> bytes:
+    """InterleavedRansEncoder::encode + finish (rans.rs:393-459)."""
+    a = np.ascontiguousarray(symbols, dtype=np.uint8).ravel()
+    out = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    _chk(lib().alo_rans_encode_interleaved(_p8(a) if a.size else None, a.size, C.byref(table), C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib().alo_free(out)
+
+
+def rans_decode_interleaved(stream: bytes, n: int, table: FreqTable) -> np.ndarray:
+    """InterleavedRansDecoder::new + decode_n (rans.rs:465-524)."""
+    buf = np.ascontiguousarray(np.frombuffer(bytes(stream), dtype=np.uint8)) if len(stream) else np.zeros(0, np.uint8)
+    out = np.empty(n, np.uint8)
+    _chk(lib().alo_rans_decode_interleaved(_p8(buf) if buf.size else None, buf.size, n, C.byref(table), _p8(out)))
     return out
 
 

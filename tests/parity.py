@@ -240,6 +240,51 @@ def check_rans_api(api, rng, n=6000):
         _check_rans(api, sy, O.build_histogram(rng.integers(0, 9, 64).astype(np.uint8)) if m == 0 else O.build_histogram(sy))
 
 
+def check_rans_interleaved(api, rng, sizes=(0, 1, 2, 3, 4, 5, 7, 1024, 4099, 70001)):
+    """InterleavedRansEncoder / Decoder (rans.rs:393-524): container bytes and decoded symbols equal the oracle's,
+    including partial decodes, hand-made containers with unequal counts (round-robin skipping) and malformed tables."""
+    # the reference's own test (rans.rs:790-803): uniform(256), 1024 symbols i % 256
+    sy = (np.arange(1024) % 256).astype(np.uint8)
+    zero_hist = np.zeros(256, np.uint32)                    # all-zero histogram -> FrequencyTable::uniform(256)
+    t = O.freq_table_from_histogram(zero_hist)
+    blob = api.rans_encode_interleaved(sy, zero_hist)
+    assert blob == O.rans_encode_interleaved(sy, t)
+    assert np.array_equal(api.rans_decode_interleaved(blob, sy.size, zero_hist), sy)
+    for n in sizes:
+        for kind in ("skewed", "flat", "malformed"):
+            if kind == "skewed":
+                sy = np.minimum(rng.geometric(0.35, n) - 1, 255).astype(np.uint8)
+            elif kind == "flat":
+                sy = rng.integers(0, 256, n, dtype=np.int64).astype(np.uint8)
+            else:   # only odd symbols in the upper range: from_histogram pushes used symbols past 4096 (SURVEY 0.7)
+                sy = (rng.integers(60, 128, n, dtype=np.int64) * 2 + 1).astype(np.uint8)
+            hist = np.bincount(sy, minlength=256).astype(np.uint32)
+            t = O.freq_table_from_histogram(hist)
+            want = O.rans_encode_interleaved(sy, t)
+            got = api.rans_encode_interleaved(sy, hist)
+            assert got == want, (n, kind)
+            for m in sorted({n, n // 2, max(n - 1, 0), min(n, 5)}):
+                assert np.array_equal(api.rans_decode_interleaved(got, m, hist), O.rans_decode_interleaved(want, m, t)), (n, kind, m)
+    # hand-made container: unequal counts, so the decoder's skip rule (rans.rs:511-513) shapes the order
+    hist = np.bincount(np.minimum(rng.geometric(0.3, 4000) - 1, 255), minlength=256).astype(np.uint32)
+    t = O.freq_table_from_histogram(hist)
+    parts, counts = [], (700, 3, 0, 1291)
+    for c in counts:
+        parts.append(O.rans_encode(np.minimum(rng.geometric(0.3, c) - 1, 255).astype(np.uint8), t))
+    blob = b"".join(len(p).to_bytes(4, "little") for p in parts) + b"".join(c.to_bytes(4, "little") for c in counts) + b"".join(parts)
+    for m in (sum(counts), 1000, 13, 12, 11, 4, 1, 0):
+        assert np.array_equal(api.rans_decode_interleaved(blob, m, hist), O.rans_decode_interleaved(blob, m, t)), m
+    # error behaviour: short header, lengths past the end, more symbols than the container holds
+    for bad, m in ((blob[:31], 1), (blob[:40], 1), (blob, sum(counts) + 1)):
+        with np.testing.assert_raises(O.OracleError):
+            O.rans_decode_interleaved(bad, m, t)
+        try:
+            api.rans_decode_interleaved(bad, m, hist)
+            raise AssertionError("ReferencePanic expected")
+        except pkg.CodecError as e:
+            assert e.kind == "ReferencePanic", e.kind
+
+
 def check_errors(api):
     """Error contract of FrameEncoder::encode / from_bytes / decode (pipeline.rs:384-427, 235-313, 562-579)."""
     enc = pkg.FrameEncoder(90, "cdf53", api=api)

@@ -233,6 +233,11 @@ def test_rans_api(api):
     parity.check_rans_api(api, np.random.default_rng(2), n=300000)
 
 
+def test_rans_interleaved(api):
+    """the reference's 4-stream container (rans.rs:393-524) over the one-warp-per-stream kernels."""
+    parity.check_rans_interleaved(api, np.random.default_rng(5), sizes=(0, 1, 2, 3, 4, 5, 7, 1024, 4099, 70001, 1 << 20))
+
+
 def test_errors_and_abi(api):
     parity.check_errors(api)
     parity.check_reference_abi(api)

@@ -26,6 +26,15 @@
 #define ALICE_FWD_M 2   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
 #endif
 
+// experiment knob: unroll factor of the steady-state row-pair loop of k_fwd_xy (unset = the compiler's choice)
+#define ALICE_PRAGMA_(x) _Pragma(#x)
+#define ALICE_PRAGMA(x) ALICE_PRAGMA_(x)
+#ifdef ALICE_XY_UNROLL
+#define ALICE_XY_UNROLL_PRAGMA ALICE_PRAGMA(unroll ALICE_XY_UNROLL)
+#else
+#define ALICE_XY_UNROLL_PRAGMA
+#endif
+
 namespace alice {
 
 // ------------------------------------------------------------------------------ k_fwd_xy
@@ -163,6 +172,7 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
         cur[0] = nxt[0]; cur[1] = nxt[1];
     }
     // steady state: the next row pair is already in flight while this one is transformed
+    ALICE_XY_UNROLL_PRAGMA
     for (; j < je; j++, k++) {
         load_pair(min(j + 1, je - 1), nxt);
         int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];

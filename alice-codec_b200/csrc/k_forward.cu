@@ -246,13 +246,15 @@ ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
 #ifndef ALICE_T_MINBLOCKS
 #define ALICE_T_MINBLOCKS 4
 #endif
-// 1: the compile-time-depth variant of k_fwd_t_quant runs a rolled, software-pipelined steady-state loop (20-31 KB of
-// code) instead of the fully unrolled one (122 KB, four times the instruction cache).  Unmeasured so far, hence off.
+// 1: the compile-time-depth variant of k_fwd_t_quant runs a rolled, software-pipelined steady-state loop (31 KB of
+// code) instead of the fully unrolled one (122 KB, four times the instruction cache).  Measured on B200 (1080p x 64,
+// CDF 9/7, whole front-end): unrolled 1.209 ms, rolled 1.122 ms, rolled with three blocks per SM (85 registers, no
+// spills) 1.106 ms (profiles/r01_ab_frontend.jsonl).
 #ifndef ALICE_T_ROLLED
-#define ALICE_T_ROLLED 0
+#define ALICE_T_ROLLED 1
 #endif
 template <int WT, int VEC, int PF>
-__global__ void ALICE_LAUNCH_BOUNDS(256, ALICE_T_MINBLOCKS)
+__global__ void ALICE_LAUNCH_BOUNDS(256, (PF != 0 && ALICE_T_ROLLED) ? 3 : ALICE_T_MINBLOCKS)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
               int pw, int ph, int f, int pf, QuantDev q, int32_t *__restrict__ coef_dump) {
     constexpr int NST = WaveletTraits<WT>::NST;

@@ -73,6 +73,7 @@ SIGNATURES = {
     "alice_codec_rdo_compute_quantizer": (cint, [dbl, i32p, u64, u8, i32p, i32p]),
     "alice_codec_rdo_estimate_variance": (cint, [i32p, u64, C.POINTER(C.c_double)]),
     "alice_codec_rdo_compute_all_quantizers": (cint, [dbl, i32p, u32, u32, u32, i32p, i32p]),
+    "alice_codec_rdo_compute_all_quantizers_device": (cint, [dbl, C.c_void_p, u32, u32, u32, i32p, i32p]),
     "alice_codec_rdo_quantize_volume": (cint, [dbl, i32p, u32, u32, u32, i32p, u64, i32p, i32p]),
     "alice_codec_psnr_device": (cint, [C.c_void_p, C.c_void_p, u64, C.c_void_p, C.POINTER(C.c_double)]),
     "alice_codec_freq_table_from_histogram": (cint, [u32p, u32, u16p, u16p, u8p]),

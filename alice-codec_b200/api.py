@@ -217,6 +217,14 @@ class Api:
                                                                   s.ctypes.data_as(_capi.i32p), d.ctypes.data_as(_capi.i32p)))
         return list(zip(s.tolist(), d.tolist()))
 
+    def rdo_compute_all_quantizers_device(self, target_bpp, d_volume: int, width, height, depth):
+        """as rdo_compute_all_quantizers for an i32 volume in device memory (raw device pointer)."""
+        s, d = np.zeros(8, np.int32), np.zeros(8, np.int32)
+        self._chk(self.lib.alice_codec_rdo_compute_all_quantizers_device(target_bpp, C.c_void_p(d_volume), width, height,
+                                                                         depth, s.ctypes.data_as(_capi.i32p),
+                                                                         d.ctypes.data_as(_capi.i32p)))
+        return list(zip(s.tolist(), d.tolist()))
+
     def rdo_quantize_volume(self, target_bpp, volume, width, height, depth):
         """statistics -> quantisers -> FastQuantizer per octant; returns (quantised i32 volume, [(step, dz)] * 8)."""
         a, pa = _i32(volume)

@@ -580,6 +580,27 @@ int alice_codec_rdo_compute_all_quantizers(double target_bpp, const int32_t *vol
     return kOk;
 }
 
+// the same for a volume that is already on the device (synchronises the default stream)
+int alice_codec_rdo_compute_all_quantizers_device(double target_bpp, const int32_t *d_volume, uint32_t w, uint32_t h,
+                                                  uint32_t d, int32_t *steps8, int32_t *dead_zones8) {
+    set_error(0, "");
+    if (!steps8 || !dead_zones8) { set_error(kErrNull, "null output"); return kErrNull; }
+    const unsigned __int128 tot = (unsigned __int128)w * h * d;
+    if (tot > ((unsigned __int128)1 << 40)) { set_error(kErrOverflow, "dimension overflow"); return kErrOverflow; }
+    double variance[8];
+    for (int i = 0; i < 8; i++) variance[i] = 1.0;
+    if (tot > 0) {
+        if (!d_volume) { set_error(kErrNull, "null argument"); return kErrNull; }
+        if (!cuda_ready()) return kErrCuda;
+        RdoViewHost v[8];
+        octant_views(d_volume, w, h, d, v);
+        int rc = rdo_variances(v, 8, variance);
+        if (rc != kOk) return rc;
+    }
+    for (int sb = 0; sb < 8; sb++) rdo_step_from_variance(target_bpp, variance[sb], sb, &steps8[sb], &dead_zones8[sb]);
+    return kOk;
+}
+
 // statistics -> quantisers -> FastQuantizer::quantize_buffer per octant (README.md:143-147 "manual pipeline", applied
 // per sub-band): out[i] = FastQuantizer::from(quantizers[octant(i)]).quantize(volume[i]).  The volume stays on the device
 // between the statistics and the quantiser pass.
@@ -977,14 +998,15 @@ int alice_codec_psnr_device(const uint8_t *d_a, const uint8_t *d_b, uint64_t len
     if (!d_a || !d_b) { set_error(kErrNull, "null argument"); return kErrNull; }
     if (!cuda_ready()) return kErrCuda;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    DevBuf acc;
-    if (!acc.alloc(8)) return kErrCuda;
-    CU_CHECK_RC(cudaMemsetAsync(acc.p, 0, 8, st));
-    sq_diff_sum_u8(d_a, d_b, (size_t)len, acc.as<unsigned long long>(), st);
+    unsigned long long *d_acc = (unsigned long long *)scratch_device(8);
+    unsigned long long *h_acc = (unsigned long long *)scratch_pinned(8);
+    if (!d_acc || !h_acc) { set_error(kErrCuda, "scratch allocation failed"); return kErrCuda; }
+    CU_CHECK_RC(cudaMemsetAsync(d_acc, 0, 8, st));
+    sq_diff_sum_u8(d_a, d_b, (size_t)len, d_acc, st);
     CU_CHECK_RC(cudaGetLastError());
-    unsigned long long sum = 0;
-    CU_CHECK_RC(cudaMemcpyAsync(&sum, acc.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK_RC(cudaMemcpyAsync(h_acc, d_acc, 8, cudaMemcpyDeviceToHost, st));
     CU_CHECK_RC(cudaStreamSynchronize(st));
+    const unsigned long long sum = *h_acc;
     const double mse = (double)sum / (double)len;
     *psnr_out = mse == 0.0 ? INFINITY : 10.0 * log10(255.0 * 255.0 / mse);
     return kOk;

@@ -302,6 +302,33 @@ void interleave_rr_u8(const uint8_t *d_planes, size_t stride, uint8_t *d_out, si
     ALICE_LAUNCH(k_interleave_rr, dim3(grid_for((long long)n, 256)), dim3(256), 0, st, d_planes, stride, d_out, n, sg);
 }
 
+namespace {
+struct ScratchBlock {
+    void *p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    bool pinned;
+    explicit ScratchBlock(bool pin) : pinned(pin) {}
+    void *get(size_t bytes) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (p && (cur != dev || cap < bytes)) {
+            if (pinned) cudaFreeHost(p); else cudaFree(p);
+            p = nullptr; cap = 0;
+        }
+        if (!p) {
+            const size_t want = bytes < 4096 ? 4096 : bytes;
+            const cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+            if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = want; dev = cur;
+        }
+        return p;
+    }
+};
+}  // namespace
+void *scratch_device(size_t bytes) { static thread_local ScratchBlock b(false); return b.get(bytes); }
+void *scratch_pinned(size_t bytes) { static thread_local ScratchBlock b(true); return b.get(bytes); }
+
 void quantize_i32(const int32_t *d_in, int32_t *d_out, size_t n, int step, int dz, int *d_panic, cudaStream_t st) {
     if (!n) return;
     ALICE_LAUNCH(k_quantize, dim3(grid_for((long long)n, 256)), dim3(256), 0, st, d_in, d_out, n, step, dz, d_panic);

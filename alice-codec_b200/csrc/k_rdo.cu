@@ -115,20 +115,32 @@ __global__ void k_rdo_mean(const RdoView *__restrict__ views, RdoState *__restri
     st[i].pos = 0;
 }
 
-// ---- genuine sequential additions for up to kRdoBlock terms from pos (one thread per view) ------------
-__global__ void k_rdo_seq(const RdoView *__restrict__ views, RdoState *__restrict__ st) {
-    if (threadIdx.x != 0) return;
+// ---- genuine sequential additions for up to kRdoBlock terms from pos (one warp per view) --------------
+// The terms are pure functions of x and the mean: all lanes compute them into shared memory, lane 0 adds them in order.
+__global__ void ALICE_LAUNCH_BOUNDS(32, 1) k_rdo_seq(const RdoView *__restrict__ views, RdoState *__restrict__ st) {
+    __shared__ double terms[kRdoBlock];
     const RdoView v = views[blockIdx.x];
-    RdoState s = st[blockIdx.x];
-    if (s.pos >= v.n) return;
+    const RdoState s = st[blockIdx.x];
+    if (s.pos >= v.n) return;                              // block-uniform
     const unsigned long long left = v.n - s.pos;
     const int count = left < (unsigned long long)kRdoBlock ? (int)left : kRdoBlock;
-    double acc = s.s;
+    const int lane = threadIdx.x;
     const double mean = s.mean;
-    rdo_for_each(v, s.pos, count, [&](int32_t x) { acc = rdo_add(acc, rdo_term(x, mean)); });
-    st[blockIdx.x].s = acc;
-    st[blockIdx.x].pos = s.pos + (unsigned long long)count;
-    st[blockIdx.x].first_nz = ~0ull;
+    {
+        const int i0 = lane * 32;                          // lane L owns terms [32L, 32L + 32)
+        if (i0 < count) {
+            int k = i0;
+            rdo_for_each(v, s.pos + (unsigned long long)i0, min(32, count - i0), [&](int32_t x) { terms[k++] = rdo_term(x, mean); });
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double acc = s.s;
+        for (int k = 0; k < count; k++) acc = rdo_add(acc, terms[k]);
+        st[blockIdx.x].s = acc;
+        st[blockIdx.x].pos = s.pos + (unsigned long long)count;
+        st[blockIdx.x].first_nz = ~0ull;
+    }
 }
 
 // ---- while the sum is still +0: skip the leading run of zero terms -----------------------------------
@@ -288,17 +300,17 @@ cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc,
         if (hv[i].n > max_n) max_n = hv[i].n;
     }
     const unsigned long long maps_per_view = (max_n + kRdoBlock - 1) / kRdoBlock + 1;
-    RdoView *d_views = nullptr;
-    RdoState *d_state = nullptr;
-    RdoMap *d_maps = nullptr;
+    // one scratch block: views | states | block maps; one pinned block for the state read-back of every pass
+    const size_t maps_off = 1024, maps_bytes = sizeof(RdoMap) * maps_per_view * (size_t)n_views;
+    unsigned char *d_scr = (unsigned char *)scratch_device(maps_off + maps_bytes);
+    RdoState *hs = (RdoState *)scratch_pinned(sizeof(RdoState) * 8);
+    if (!d_scr || !hs) return cudaErrorMemoryAllocation;
+    static_assert(sizeof(RdoView) * 8 + sizeof(RdoState) * 8 <= 1024, "scratch header too small");
+    RdoView *d_views = (RdoView *)d_scr;
+    RdoState *d_state = (RdoState *)(d_scr + sizeof(RdoView) * 8);
+    RdoMap *d_maps = (RdoMap *)(d_scr + maps_off);
     cudaError_t e;
-    auto fail = [&](cudaError_t err) {
-        cudaFree(d_views); cudaFree(d_state); cudaFree(d_maps);
-        return err;
-    };
-    if ((e = cudaMalloc(&d_views, sizeof(RdoView) * 8)) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&d_state, sizeof(RdoState) * 8)) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&d_maps, sizeof(RdoMap) * maps_per_view * n_views)) != cudaSuccess) return fail(e);
+    auto fail = [&](cudaError_t err) { return err; };
     if ((e = cudaMemcpyAsync(d_views, hv, sizeof(RdoView) * n_views, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
     if ((e = cudaMemsetAsync(d_state, 0, sizeof(RdoState) * 8, st)) != cudaSuccess) return fail(e);
     const int gx = (int)std::min<unsigned long long>((max_n + 255) / 256, (unsigned long long)kNumSMs * 8);
@@ -306,7 +318,6 @@ cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc,
         ALICE_LAUNCH(k_rdo_sum, dim3(gx ? gx : 1, n_views), dim3(256), 0, st, d_views, d_state);
     }
     ALICE_LAUNCH(k_rdo_mean, dim3(1), dim3(32), 0, st, d_views, d_state, n_views);
-    RdoState hs[8];
     for (int guard = 0;; guard++) {
         ALICE_LAUNCH(k_rdo_seq, dim3(n_views), dim3(32), 0, st, d_views, d_state);
         ALICE_LAUNCH(k_rdo_first_nonzero, dim3(gx ? gx : 1, n_views), dim3(256), 0, st, d_views, d_state);
@@ -323,7 +334,6 @@ cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc,
         if (guard > (1 << 22)) return fail(cudaErrorUnknown);   // every pass consumes at least one block per view
     }
     for (int i = 0; i < n_views; i++) { h_acc[i] = hs[i].s; h_mean[i] = hs[i].mean; }
-    cudaFree(d_views); cudaFree(d_state); cudaFree(d_maps);
     return cudaGetLastError();
 }
 

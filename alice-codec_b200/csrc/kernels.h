@@ -95,6 +95,12 @@ cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc,
 void rdo_quantize_volume(const int32_t *d_in, int32_t *d_out, unsigned w, unsigned h, unsigned d, const int dz[8],
                          const unsigned long long recip[8], const unsigned shift[8], cudaStream_t st);
 
+// ---- small per-thread scratch (k_generic.cu): cudaMalloc / cudaFree cost milliseconds next to other contexts' memory,
+// so short reductions keep one growing device block and one pinned host block per calling thread and device.
+// Returns nullptr if the allocation fails.  The blocks live until the thread's next request on another device.
+void *scratch_device(size_t bytes);
+void *scratch_pinned(size_t bytes);
+
 // ---- synthetic inputs (k_synth.cu) ---------------------------------
 void synth_rgb(int kind, uint32_t seed, int w, int h, int f, uint8_t *d_rgb, cudaStream_t st);
 

@@ -133,6 +133,9 @@ int alice_codec_rdo_estimate_variance(const int32_t *coeffs, uint64_t n, double 
  * octant is bit-identical to the reference's sequential loop (quant.rs:425-432). */
 int alice_codec_rdo_compute_all_quantizers(double target_bpp, const int32_t *volume, uint32_t width, uint32_t height,
                                            uint32_t depth, int32_t *steps8, int32_t *dead_zones8);
+/* the same for a volume already in device memory */
+int alice_codec_rdo_compute_all_quantizers_device(double target_bpp, const int32_t *d_volume, uint32_t width,
+                                                  uint32_t height, uint32_t depth, int32_t *steps8, int32_t *dead_zones8);
 /* statistics -> quantisers -> FastQuantizer::quantize_buffer (quant.rs:272-299) with the constants of each
  * element's octant, the volume staying on the device in between; also returns the 8 (step, dead_zone) pairs */
 int alice_codec_rdo_quantize_volume(double target_bpp, const int32_t *volume, uint32_t width, uint32_t height,

@@ -299,7 +299,7 @@ def main():
     by_kernel = {
         "frontend": rl("encode front-end: k_fwd_xy + k_fwd_t_quant + k_hist_zero_bin per chunk, summed over the batch",
                        alg_bytes, fe_ms, traffic.get("frontend_dram_bytes_per_chunk", 0) * B or None,
-                       "6 B/px algorithmic (3 in + 3 out); INT32-issue bound, see DESIGN.md 4.2"),
+                       "6 B/px algorithmic (3 in + 3 out); latency and issue bound, not HBM bound: see DESIGN.md 4.2 and profiles/r01_pipe_stall_analysis.md"),
         "backend": rl("decode back-end: k_inv_t + k_inv_yx per chunk, summed over the batch", alg_bytes, be_ms,
                       traffic.get("backend_dram_bytes_per_chunk", 0) * B or None, "6 B/px algorithmic"),
         "rans_encode": rl("k_rans_encode (one launch, 3 streams per chunk)", n_sym + payload_bytes, enc_ms, None,

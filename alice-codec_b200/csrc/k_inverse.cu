@@ -34,6 +34,11 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 // k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
 template <bool WIDE> struct Handoff { typedef int32_t T; };
 
+// 1: 64-frame chunks use the rolled, software-pipelined compile-time-depth variant of k_inv_t (see the kernel)
+#ifndef ALICE_INV_T_ROLLED
+#define ALICE_INV_T_ROLLED 0
+#endif
+
 template <int WT, int VEC, int PF, bool WIDE>
 __global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 3 : 4))
 k_inv_t(const uint8_t *__restrict__ symbols, void *__restrict__ coef_v, int pw, int ph, int f, int pf, int step0,
@@ -72,16 +77,63 @@ k_inv_t(const uint8_t *__restrict__ symbols, void *__restrict__ coef_v, int pw, 
         const size_t off = (size_t)item * VEC;
         InvLift<WT, WIDE> L[VEC];
         int k = 0;
+        struct RawPair { uint32_t a, b; };              // VEC symbols of frame j (low) and of frame halft + j (high)
+        auto load_at = [&](const uint8_t *pl, const uint8_t *ph_) {
+            RawPair r;
+            if (VEC == 4) {
+                r.a = __ldg(reinterpret_cast<const uint32_t *>(pl));
+                r.b = __ldg(reinterpret_cast<const uint32_t *>(ph_));
+            } else {
+                r.a = __ldg(reinterpret_cast<const uint16_t *>(pl));
+                r.b = __ldg(reinterpret_cast<const uint16_t *>(ph_));
+            }
+            return r;
+        };
+        if (PF != 0) {
+            // compile-time depth: unrolled prologue (warm-up, mirrored left edge), then a ROLLED steady-state loop with
+            // the symbols of the next two pairs in flight (the fully unrolled form spilled 1.4-1.9 KB per thread and
+            // overflowed the instruction cache; the generic runtime loop below tests k and j in every iteration and
+            // waits on every load: long_scoreboard was its dominant stall)
+            static_assert(PF == 0 || PF / 2 >= NST + 4, "compile-time depth too short for the pipelined form");
+            const uint8_t *pl = src + off, *ph_ = src + (size_t)halft * frame_sz + off;
+            RawPair r0 = load_at(pl, ph_);
+            pl += frame_sz; ph_ += frame_sz;
+            RawPair r1 = load_at(pl, ph_);
+            pl += frame_sz; ph_ += frame_sz;
+            RawPair r2 = r1;
+            auto step_pair = [&](int j, bool steady) {
+                int ev[VEC], od[VEC];
+                bool has = steady;
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    const int lo = sym_to_coef((r0.a >> (8 * i)) & 0xff, step);
+                    const int hi = sym_to_coef((r0.b >> (8 * i)) & 0xff, step);
+                    if (steady) L[i].push_steady(lo, hi, ev[i], od[i]);
+                    else has = L[i].push(lo, hi, j, j, ev[i], od[i]);
+                }
+                if (has) emit(off, j - NST, ev, od);
+                r0 = r1; r1 = r2;
+            };
+#pragma unroll
+            for (int j = 0; j <= NST; j++) {
+                r2 = load_at(pl, ph_);                  // pair j + 2 <= NST + 2 < halft
+                pl += frame_sz; ph_ += frame_sz;
+                step_pair(j, false);
+            }
+#pragma unroll 1
+            for (int j = NST + 1; j < halft - 2; j++) {
+                r2 = load_at(pl, ph_);                  // pair j + 2 <= halft - 1
+                pl += frame_sz; ph_ += frame_sz;
+                step_pair(j, true);
+            }
+            step_pair(halft - 2, true);
+            step_pair(halft - 1, true);
+            k = halft;
+        } else
 #pragma unroll
         for (int j = 0; j < halft; j++, k++) {
-            uint32_t a, b;
-            if (VEC == 4) {
-                a = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)j * frame_sz + off));
-                b = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(halft + j) * frame_sz + off));
-            } else {
-                a = __ldg(reinterpret_cast<const uint16_t *>(src + (size_t)j * frame_sz + off));
-                b = __ldg(reinterpret_cast<const uint16_t *>(src + (size_t)(halft + j) * frame_sz + off));
-            }
+            const RawPair r = load_at(src + (size_t)j * frame_sz + off, src + (size_t)(halft + j) * frame_sz + off);
+            const uint32_t a = r.a, b = r.b;
             int ev[VEC], od[VEC];
             bool has = false;
 #pragma unroll
@@ -261,7 +313,10 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
         const dim3 tgrid(gx, 1, 3), tblock(256);
         // (a fully unrolled PF = 64 instantiation spills 1.4-1.9 KB per thread and measured 2.3x slower than the
         //  runtime loop, so the inverse t pass always uses PF = 0)
-        if (vec == 4) {
+        if (vec == 4 && pf == 64 && ALICE_INV_T_ROLLED) {
+            auto kt = k_inv_t<WT, 4, 64, WIDE>;
+            ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
+        } else if (vec == 4) {
             auto kt = k_inv_t<WT, 4, 0, WIDE>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
         } else {

@@ -144,6 +144,17 @@ template <int WT, bool WIDE> struct InvLift {
         ep2 = e2n; op2 = a_o;
         return true;
     }
+    // push() for k > NST and j > NST: no warm-up and no left-edge mirror, the pair j-NST always comes out
+    ALICE_HD void push_steady(int en, int on, int &ev, int &od) {
+        constexpr int SA = NST - 1;
+        const int e1 = upd(en, on, op, false, coef_u<WT>(SA));
+        const int a_e = ep, a_o = prd(op, ep, e1, coef_p<WT>(SA));
+        ep = e1; op = on;
+        if (NST == 1) { ev = a_e; od = a_o; return; }
+        const int e2n = upd(a_e, a_o, op2, false, coef_u<WT>(0));
+        ev = ep2; od = prd(op2, ep2, e2n, coef_p<WT>(0));
+        ep2 = e2n; op2 = a_o;
+    }
     ALICE_HD bool flush(int k, int which, int half, int &ev, int &od) {
         constexpr int SA = NST - 1;
         if (NST == 1) { ev = ep; od = prd(op, ep, ep, coef_p<WT>(SA)); return true; }

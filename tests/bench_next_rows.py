@@ -1,6 +1,6 @@
 """Measurements for the SURVEY.md 8(f) rows beside the hot path (RDO statistics, device PSNR, interleaved rANS),
 each through the C ABI with HOST buffers (copies included), next to the C oracle on one host core.
-Prints one JSON line per row; run on a GPU box:  python tools/bench_next_rows.py > gpurun_out/next_rows.jsonl"""
+Prints one JSON line per row; run on a GPU box:  python tests/bench_next_rows.py > gpurun_out/next_rows.jsonl"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (the checker and the CPU baseline leg)

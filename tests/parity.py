@@ -341,15 +341,17 @@ def check_decode_foreign_headers(api, rng):
     assert np.array_equal(out, O.decode(bytes(alc)))
     # largest coefficients the 32-bit / i16 decode variant accepts (128 * |step| <= 15000) on full-range symbols
     # (noise at step 1 wraps through all 256 symbols), and just beyond it (wide variant), for every wavelet
+    # (the 64-frame shape runs the compile-time-depth variants of the temporal kernels)
     for wv in (0, 1, 2):
-        base = O.encode(O.generate(O.G2, 36, 20, 8), 36, 20, 8, 100, wv)
-        for steps in ((117, -117, 110), (118, 117, 117), (64, 64, 64)):
-            alc = bytearray(base)
-            for c, step in enumerate(steps):
-                off = 18 + c * 1040 + 4
-                alc[off:off + 4] = int(step).to_bytes(4, "little", signed=True)
-            out = pkg.FrameDecoder(api=api).decode(pkg.EncodedChunk.from_bytes(bytes(alc), api=api))
-            assert np.array_equal(out, O.decode(bytes(alc))), (wv, steps)
+        for (w, h, f) in ((36, 20, 8), (12, 4, 64)):
+            base = O.encode(O.generate(O.G2, w, h, f), w, h, f, 100, wv)
+            for steps in ((117, -117, 110), (118, 117, 117), (64, 64, 64)):
+                alc = bytearray(base)
+                for c, step in enumerate(steps):
+                    off = 18 + c * 1040 + 4
+                    alc[off:off + 4] = int(step).to_bytes(4, "little", signed=True)
+                out = pkg.FrameDecoder(api=api).decode(pkg.EncodedChunk.from_bytes(bytes(alc), api=api))
+                assert np.array_equal(out, O.decode(bytes(alc))), (wv, steps, f)
 
 
 def check_reference_abi(api):

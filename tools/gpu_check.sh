@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${
 timeout 480 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
-timeout 150 python tools/bench_next_rows.py > gpurun_out/${tag}_next_rows.jsonl 2> gpurun_out/${tag}_next_rows.err
+timeout 150 python tests/bench_next_rows.py > gpurun_out/${tag}_next_rows.jsonl 2> gpurun_out/${tag}_next_rows.err
 cat gpurun_out/${tag}_next_rows.jsonl
 timeout 150 python tools/ab_frontend.py base t_rolled t_rolled3 xyu2 xyu4 base > gpurun_out/${tag}_ab_frontend.jsonl 2> gpurun_out/${tag}_ab_frontend.err
 cat gpurun_out/${tag}_ab_frontend.jsonl

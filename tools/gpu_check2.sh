@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 420 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
-timeout 150 python tools/bench_next_rows.py > gpurun_out/${tag}_next_rows.jsonl 2> gpurun_out/${tag}_next_rows.err
+timeout 150 python tests/bench_next_rows.py > gpurun_out/${tag}_next_rows.jsonl 2> gpurun_out/${tag}_next_rows.err
 cat gpurun_out/${tag}_next_rows.jsonl
 timeout 400 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 echo "bench rc=$?"; cat gpurun_out/${tag}_bench.json

@@ -34,9 +34,10 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 // k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
 template <bool WIDE> struct Handoff { typedef int32_t T; };
 
-// 1: 64-frame chunks use the rolled, software-pipelined compile-time-depth variant of k_inv_t (see the kernel)
+// 1: 64-frame chunks use the rolled, software-pipelined compile-time-depth variant of k_inv_t (see the kernel).
+// Measured on B200 (1080p x 64, CDF 9/7, whole back-end): 1.666 -> 1.600 ms (profiles/r01_ab_backend.jsonl).
 #ifndef ALICE_INV_T_ROLLED
-#define ALICE_INV_T_ROLLED 0
+#define ALICE_INV_T_ROLLED 1
 #endif
 
 template <int WT, int VEC, int PF, bool WIDE>
@@ -311,8 +312,8 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
         const long long items = frame_sz / vec;
         const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
         const dim3 tgrid(gx, 1, 3), tblock(256);
-        // (a fully unrolled PF = 64 instantiation spills 1.4-1.9 KB per thread and measured 2.3x slower than the
-        //  runtime loop, so the inverse t pass always uses PF = 0)
+        // (a FULLY unrolled PF = 64 instantiation spilled 1.4-1.9 KB per thread and measured 2.3x slower than the
+        //  runtime loop; the rolled compile-time-depth form is 4 % faster than the runtime loop on the whole back-end)
         if (vec == 4 && pf == 64 && ALICE_INV_T_ROLLED) {
             auto kt = k_inv_t<WT, 4, 64, WIDE>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);

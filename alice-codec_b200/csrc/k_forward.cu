@@ -253,10 +253,6 @@ ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
 #ifndef ALICE_T_ROLLED
 #define ALICE_T_ROLLED 1
 #endif
-// 1: the histogram update tests the packed word of VEC symbols before the single symbols (zeros come in runs)
-#ifndef ALICE_HIST_WORD_SKIP
-#define ALICE_HIST_WORD_SKIP 0
-#endif
 template <int WT, int VEC, int PF>
 __global__ void ALICE_LAUNCH_BOUNDS(256, (PF != 0 && ALICE_T_ROLLED) ? 3 : ALICE_T_MINBLOCKS)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
@@ -275,24 +271,6 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
 
     auto emit = [&](size_t off, int jo, const int (&lo)[VEC], const int (&hi)[VEC]) {
         uint32_t pl = 0, phh = 0;
-#if ALICE_HIST_WORD_SKIP
-        uint32_t sls[VEC], shs[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; i++) {
-            sls[i] = quant_symbol(lo[i], q); shs[i] = quant_symbol(hi[i], q);
-            pl |= sls[i] << (8 * i);
-            phh |= shs[i] << (8 * i);
-        }
-        // bin 0 is filled in afterwards (N - sum of the others); zeros come in runs, so whole words are tested first
-        if (pl) {
-#pragma unroll
-            for (int i = 0; i < VEC; i++) if (sls[i]) atomicAdd(&sh_hist[sls[i]], 1u);
-        }
-        if (phh) {
-#pragma unroll
-            for (int i = 0; i < VEC; i++) if (shs[i]) atomicAdd(&sh_hist[shs[i]], 1u);
-        }
-#else
 #pragma unroll
         for (int i = 0; i < VEC; i++) {
             uint32_t sl = quant_symbol(lo[i], q), sh = quant_symbol(hi[i], q);
@@ -301,7 +279,6 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
             if (sl) atomicAdd(&sh_hist[sl], 1u);   // bin 0 is filled in afterwards: N - sum of the others
             if (sh) atomicAdd(&sh_hist[sh], 1u);
         }
-#endif
         if (coef_dump) {  // parity-test stage dump of the 3-D coefficients (null in production)
             int32_t *cd = coef_dump + (size_t)c * pf * frame_sz;
 #pragma unroll

@@ -17,6 +17,8 @@
 //   k_inv_yx    mirror of k_fwd_xy: one warp per column strip marching down y; streaming
 //               inverse y lifting per owned column, lane-parallel inverse x lifting with
 //               shuffles, then crop, i16 truncation, inverse colour transform and RGB store.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "lifting.cuh"
 
@@ -34,6 +36,11 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 // k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
 template <bool WIDE> struct Handoff { typedef int32_t T; };
 
+// 1: k_inv_yx prefetches the next row pair, takes unchecked 8-byte loads on interior strips and runs the steady-state
+// lifting form after the warm-up (emulator parity green; not yet measured on hardware, hence off)
+#ifndef ALICE_YX_PREFETCH
+#define ALICE_YX_PREFETCH 0
+#endif
 // 1: 64-frame chunks use the rolled, software-pipelined compile-time-depth variant of k_inv_t (see the kernel).
 // Measured on B200 (1080p x 64, CDF 9/7, whole back-end): 1.666 -> 1.600 ms (profiles/r01_ab_backend.jsonl).
 #ifndef ALICE_INV_T_ROLLED
@@ -253,6 +260,79 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
         }
     };
 
+#if ALICE_YX_PREFETCH
+    // The row pair j + 1 is loaded before pair j is transformed (the kernel's dominant stall was long_scoreboard: every
+    // iteration waited for its own loads), strips whose 32 lanes are all inside the row use plain 8-byte loads without
+    // range or alignment tests, and after the warm-up the lifting state machine runs its branch-free steady form.
+    const bool fast_ld = M == 2 && sizeof(HT) == 4 && sx * VPAIRS - M >= 0 && sx * VPAIRS - M + 32 * M <= halfx &&
+                         (halfx & 1) == 0 && (pw & 1) == 0 && (reinterpret_cast<uintptr_t>(coef) & 7) == 0;
+    auto load_rows = [&](int j, int (&lo)[3][PXL], int (&hi)[3][PXL]) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const HT *row_lo = in_t + c * plane_sz + (size_t)j * pw;
+            const HT *row_hi = in_t + c * plane_sz + (size_t)(halfy + j) * pw;
+            if (fast_ld) {
+#ifdef ALICE_EMUL
+                if (((reinterpret_cast<uintptr_t>(row_lo + p0) | reinterpret_cast<uintptr_t>(row_lo + halfx + p0) |
+                      reinterpret_cast<uintptr_t>(row_hi + p0) | reinterpret_cast<uintptr_t>(row_hi + halfx + p0)) & 7) != 0 ||
+                    p0 < 0 || p0 + M > halfx || j < 0 || j >= halfy)
+                    abort();   // the emulator does not fault on what the GPU would
+#endif
+                const int2 a = __ldg(reinterpret_cast<const int2 *>(row_lo + p0));
+                const int2 b = __ldg(reinterpret_cast<const int2 *>(row_lo + halfx + p0));
+                const int2 c2 = __ldg(reinterpret_cast<const int2 *>(row_hi + p0));
+                const int2 d = __ldg(reinterpret_cast<const int2 *>(row_hi + halfx + p0));
+                lo[c][0] = a.x; lo[c][1] = a.y; lo[c][PXL - 2] = b.x; lo[c][PXL - 1] = b.y;
+                hi[c][0] = c2.x; hi[c][1] = c2.y; hi[c][PXL - 2] = d.x; hi[c][PXL - 1] = d.y;
+            } else {
+                int t0[M], t1[M], t2[M], t3[M];
+                load_group_i32<M, HT>(row_lo, p0, halfx, t0);
+                load_group_i32<M, HT>(row_lo + halfx, p0, halfx, t1);
+                load_group_i32<M, HT>(row_hi, p0, halfx, t2);
+                load_group_i32<M, HT>(row_hi + halfx, p0, halfx, t3);
+#pragma unroll
+                for (int i = 0; i < M; i++) { lo[c][i] = t0[i]; lo[c][M + i] = t1[i]; hi[c][i] = t2[i]; hi[c][M + i] = t3[i]; }
+            }
+        }
+    };
+    auto emit_pair = [&](int jo, int (&ev)[3][PXL], int (&od)[3][PXL]) {
+        const bool active = jo >= i0 && jo < i1;
+        emit_row(2 * jo, active, ev);
+        emit_row(2 * jo + 1, active, od);
+    };
+    int k = 0;
+    int j = js;
+    int clo[3][PXL], chi[3][PXL], nlo[3][PXL], nhi[3][PXL];
+    if (js < je) load_rows(js, clo, chi);
+    auto rotate = [&]() {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) { clo[c][i] = nlo[c][i]; chi[c][i] = nhi[c][i]; }
+    };
+    // warm-up: the first NST + 1 pairs go through the general push (mirrored left edge when js == 0)
+    for (; j < je && k <= NST; j++, k++) {
+        load_rows(min(j + 1, je - 1), nlo, nhi);
+        int ev[3][PXL], od[3][PXL];
+        bool has = false;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) has = L[c][i].push(clo[c][i], chi[c][i], k, j, ev[c][i], od[c][i]);
+        if (has) emit_pair(j - NST, ev, od);
+        rotate();
+    }
+    for (; j < je; j++, k++) {
+        load_rows(min(j + 1, je - 1), nlo, nhi);
+        int ev[3][PXL], od[3][PXL];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < PXL; i++) L[c][i].push_steady(clo[c][i], chi[c][i], ev[c][i], od[c][i]);
+        emit_pair(j - NST, ev, od);
+        rotate();
+    }
+#else
     int k = 0;
     for (int j = js; j < je; j++, k++) {
         int ev[3][PXL], od[3][PXL];
@@ -276,6 +356,7 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
             emit_row(2 * jo + 1, active, od);
         }
     }
+#endif
     if (je == halfy) {
 #pragma unroll
         for (int which = 0; which < NST; which++) {

@@ -41,6 +41,22 @@ def test_noise_and_extreme_quality(api, kind, quality):
         parity.check_encode_decode(api, kind, 24, 10, 6, quality, wavelet)
 
 
+def test_random_shapes(api):
+    """seeded random (shape, wavelet, quality, input kind) cases: strips with and without interior lanes, 1-frame
+    to 66-frame chunks (the 64-deep chunks run the compile-time-depth temporal kernels), every stage compared"""
+    rng = np.random.default_rng(20261018)
+    done = 0
+    while done < 24:
+        w = int(rng.choice([rng.integers(1, 40), rng.integers(40, 300), rng.integers(240, 520)]))
+        h = int(rng.integers(1, 48))
+        f = int(rng.choice([1, 2, 3, 5, 7, 62, 63, 64, 65, 66]))
+        if w * h * f > 300000:
+            continue
+        parity.check_encode_decode(api, int(rng.choice([O.G0, O.G1, O.G2])), w, h, f,
+                                   int(rng.choice([0, 30, 75, 80, 90, 100])), int(rng.integers(0, 3)))
+        done += 1
+
+
 def test_stage_apis(api):
     rng = np.random.default_rng(1)
     parity.check_wavelet_api(api, rng, [2, 3, 8, 9, 31], [(4, 4), (5, 3), (16, 9)], [(4, 4, 4), (5, 3, 2), (8, 6, 3)])

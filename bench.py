@@ -269,6 +269,16 @@ def main():
                 alc = batch.get_chunk(0).to_bytes()
                 bit_exact = (hashlib.sha256(alc).hexdigest() == g["sha256_alc"] and
                              hashlib.sha256(d_out[0].cpu().numpy().tobytes()).hexdigest() == g["sha256_decoded"])
+    # alice_codec_psnr (ffi.rs:270) of chunk 0's decode against its input, computed on the device (outside the timed
+    # region).  Informational: the reference's decode of its own stream is not a reconstruction and the
+    # CUDA path reproduces exactly that output, so a low figure here is the reference's, not a defect.
+    psnr_db = None
+    if rank == 0:
+        try:
+            psnr_db = round(api.psnr_device(d_in[0].data_ptr(), d_out[0].data_ptr(), int(d_in[0].numel()),
+                                            stream.cuda_stream), 3)
+        except Exception:
+            psnr_db = None
 
     # ---- rooflines, from the library's own CUDA events on the launch stream (averaged over the timed steps).
     # `roofline` describes the DOMINANT kernel of the step by device time (the rANS decode launch: one warp per
@@ -426,7 +436,8 @@ def main():
                            "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective"},
                 "e2e": e2e, "gpu_launches": args.steps * (5 * B + 4), "roofline": roofline, "roofline_by_kernel": by_kernel,
                 "stages": stages,
-                "cpu_baseline": cpu, "clocks": sampler.summary(), "bit_exact_vs_oracle_digest": bit_exact}
+                "cpu_baseline": cpu, "clocks": sampler.summary(), "bit_exact_vs_oracle_digest": bit_exact,
+                "psnr_decoded_vs_input_db": psnr_db}
         print(json.dumps(line), flush=True)
     if batch is not None:
         batch.close()

@@ -31,6 +31,8 @@
 // bytes come from a shared "window" table holding, for every byte position, the next eight
 // bytes as two big-endian words (8 bytes per position: the renormalisation shift in bits is
 // the address increment), so renormalisation is two selects and one funnel shift.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace alice {
@@ -416,10 +418,15 @@ constexpr int kDecBlock = 256;                   // symbols per fast block (one 
 constexpr int kWinPos = 1024;                    // byte positions held by the window ring
 constexpr int kWinMirror = 2 * kDecBlock + 16;   // positions mirrored past the end: a block reads linearly
 constexpr int kWinFill = 256;                    // bytes converted per refill (8 per lane)
+constexpr bool kDecSplit16Default = false;       // see kDecSmemBytes16
 // (48.9 KB per block in total, so four decode blocks fit the 227 KB of an SM: 592 concurrent streams)
 // window entry of position p: {bytes p..p+3, bytes p+4..p+7} as two big-endian words; 8 bytes per position makes
 // the renormalisation shift (8 bits per byte) equal to the address increment
 constexpr int kDecSmemBytes = kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
+// SPLIT16 layout: {freq} and {slot - cum} as two u16 tables (16 KB instead of 32 KB; the two 2-byte loads zero-extend
+// for free, so the dependent chain LDS -> IMAD is unchanged): 33.3 KB per stream, six streams per SM instead of four.
+// Off by default until measured (ALICE_RANS_DEC_SPLIT16=1 selects it at run time).
+constexpr int kDecSmemBytes16 = kDecLutEntries * 4 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
 
 struct DecState {
     uint32_t x;
@@ -428,10 +435,15 @@ struct DecState {
 };
 
 // generic step (rans.rs:351-371 literally), reading stream bytes from global memory
-ALICE_D uint32_t dec_step_generic(DecState &s, const uint2 *ent, const uint8_t *symt, uint32_t wide_sym,
+template <bool SPLIT16>
+ALICE_D uint32_t dec_step_generic(DecState &s, const void *tab, const uint8_t *symt, uint32_t wide_sym,
                                   uint32_t wide_freq) {
     const uint32_t slot = s.x & (kProbScale - 1);
-    const uint2 e = ent[slot];
+    uint2 e;
+    if (SPLIT16) {
+        const uint16_t *f16 = reinterpret_cast<const uint16_t *>(tab);
+        e = make_uint2(f16[slot], f16[kDecLutEntries + slot]);
+    } else e = reinterpret_cast<const uint2 *>(tab)[slot];
     const uint32_t sym = symt[slot];
     const uint32_t f = (sym == wide_sym) ? wide_freq : e.x;
     s.x = f * (s.x >> kProbBits) + e.y;          // low 32 bits of the reference's u64 expression
@@ -442,17 +454,21 @@ ALICE_D uint32_t dec_step_generic(DecState &s, const uint2 *ent, const uint8_t *
     return sym;
 }
 
-template <int LPB>
+template <int LPB, bool SPLIT16>
 __global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
               const DecAux *__restrict__ aux_all, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
     const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
     if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
-    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kDecSmemBytes;
+    constexpr int kTabBytes = SPLIT16 ? kDecLutEntries * 4 : kDecLutEntries * 8;
+    constexpr int SH = SPLIT16 ? 1 : 3;              // log2 of the table stride in bytes: slot << SH addresses the table(s)
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * (SPLIT16 ? kDecSmemBytes16 : kDecSmemBytes);
     uint2 *ent = reinterpret_cast<uint2 *>(smem);                               // slot -> {freq, slot - cum}
-    uint2 *win = reinterpret_cast<uint2 *>(smem + kDecLutEntries * 8);          // position -> next 8 bytes, big-endian
-    uint8_t *symt = smem + kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8;     // slot -> symbol
+    uint16_t *f16 = reinterpret_cast<uint16_t *>(smem);                         // SPLIT16: slot -> freq ...
+    uint16_t *b16 = f16 + kDecLutEntries;                                       //          ... and slot -> slot - cum
+    uint2 *win = reinterpret_cast<uint2 *>(smem + kTabBytes);                   // position -> next 8 bytes, big-endian
+    uint8_t *symt = smem + kTabBytes + (kWinPos + kWinMirror) * 8;              // slot -> symbol
     uint16_t *slots = reinterpret_cast<uint16_t *>(symt + kDecLutEntries);      // slots decoded in this block
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;
@@ -460,7 +476,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         const uint32_t *src = lut_all + (size_t)stream * kDecLutEntries;
         for (int i = lane; i < kDecLutEntries; i += 32) {
             const uint32_t p = src[i];
-            ent[i] = make_uint2(((p >> 8) & 0xfffu) + 1u, p >> 20);
+            if (SPLIT16) { f16[i] = (uint16_t)(((p >> 8) & 0xfffu) + 1u); b16[i] = (uint16_t)(p >> 20); }
+            else ent[i] = make_uint2(((p >> 8) & 0xfffu) + 1u, p >> 20);
             symt[i] = (uint8_t)p;
         }
     }
@@ -493,7 +510,7 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
     auto careful = [&](unsigned long long upto) {   // generic steps for symbols [i, upto); true if the rest was filled
         for (; i < upto; i++) {
             const uint32_t xb = s.x;
-            const uint32_t sy = dec_step_generic(s, ent, symt, aux.wide_sym, aux.wide_freq);
+            const uint32_t sy = dec_step_generic<SPLIT16>(s, smem, symt, aux.wide_sym, aux.wide_freq);
             if (lane0) out[i] = (uint8_t)sy;
             if (s.pos >= s.len && s.x == xb) {
                 // exhausted stream and a fixed point of the state map: every further symbol is `sy`
@@ -559,21 +576,25 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         // ---- lane 0 only (one active lane: every shared access is a single wavefront)
         if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
-            uint32_t x3 = x << 3;                             // the state shifted by 3: its low bits address ent[]
+            uint32_t x3 = x << SH;                            // the state shifted by SH: its low bits address the table
             for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
-                    const uint32_t slot8 = x3 & ((kProbScale - 1) << 3);           // byte offset of ent[slot]
+                    const uint32_t slot8 = x3 & ((kProbScale - 1) << SH);          // byte offset of the slot's entry
                     const uint32_t xs = x >> kProbBits;
-                    const uint2 e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
+                    uint2 e;
+                    if (SPLIT16) {
+                        e.x = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(f16) + slot8);
+                        e.y = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(b16) + slot8);
+                    } else e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
                     slots[g * 16 + b] = (uint16_t)slot8;
                     x = e.x * xs + e.y;
                     // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
                     const bool ka = x < kRansL, kb = x < (1u << 15);
-                    uint32_t sa = ka ? 8u : 0u, sa3 = ka ? 11u : 3u;
+                    uint32_t sa = ka ? 8u : 0u, sa3 = ka ? 8u + SH : (uint32_t)SH;
                     sa = kb ? 16u : sa;
-                    sa3 = kb ? 19u : sa3;
+                    sa3 = kb ? 16u + SH : sa3;
                     x3 = __funnelshift_l(v, x, sa3);          // (renormalised x) << 3, without waiting for it
                     x = __funnelshift_l(v, x, sa);
                     v = __funnelshift_l(lo, v, sa);
@@ -594,8 +615,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             uint32_t ow[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> 3], b2 = symt[sw[2 * k] >> 19];
-                const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> 3], d2 = symt[sw[2 * k + 1] >> 19];
+                const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> SH], b2 = symt[sw[2 * k] >> (16 + SH)];
+                const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> SH], d2 = symt[sw[2 * k + 1] >> (16 + SH)];
                 ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
             }
             *reinterpret_cast<uint2 *>(out + i + 8 * lane) = make_uint2(ow[0], ow[1]);
@@ -608,15 +629,21 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
                  cudaStream_t st) {
     if (n_streams <= 0) return;
+    const char *env = getenv("ALICE_RANS_DEC_SPLIT16");
+    const bool split16 = env ? env[0] == '1' : kDecSplit16Default;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        const int smem = LPB * kDecSmemBytes;
+        auto go = [&](auto k, int smem, unsigned long long &attr_done) {
 #ifndef ALICE_EMUL
-        static unsigned long long attr_done = 0;
-        ensure_dyn_smem(k_rans_decode<LPB>, smem, attr_done);
+            ensure_dyn_smem(k, smem, attr_done);
+#else
+            (void)attr_done;
 #endif
-        auto k = k_rans_decode<LPB>;
-        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
+            ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
+        };
+        static unsigned long long done_plain = 0, done_split = 0;
+        if (split16) go(k_rans_decode<LPB, true>, LPB * kDecSmemBytes16, done_split);
+        else go(k_rans_decode<LPB, false>, LPB * kDecSmemBytes, done_plain);
     });
 }
 

@@ -89,6 +89,17 @@ def test_rans_api(api):
     parity.check_rans_api(api, np.random.default_rng(2), n=3000)
 
 
+def test_rans_decode_split16_layout(api, monkeypatch):
+    """the 16-bit split decode tables (33 KB per stream, six streams per SM; off by default until measured) decode
+    exactly like the 8-byte entries: rANS API cases, malformed tables included, and whole chunks"""
+    monkeypatch.setenv("ALICE_RANS_DEC_SPLIT16", "1")
+    parity.check_rans_api(api, np.random.default_rng(2), n=3000)
+    for wavelet in (0, 1, 2):
+        parity.check_encode_decode(api, O.G1, 260, 4, 64, 80, wavelet)
+        parity.check_encode_decode(api, O.G2, 24, 10, 6, 100, wavelet)
+    parity.check_decode_foreign_headers(api, np.random.default_rng(3))
+
+
 def test_rans_interleaved(api):
     parity.check_rans_interleaved(api, np.random.default_rng(5), sizes=(0, 1, 2, 3, 4, 5, 7, 1024, 4099))
 

@@ -260,7 +260,16 @@ def check_rans_interleaved(api, rng, sizes=(0, 1, 2, 3, 4, 5, 7, 1024, 4099, 700
                 sy = (rng.integers(60, 128, n, dtype=np.int64) * 2 + 1).astype(np.uint8)
             hist = np.bincount(sy, minlength=256).astype(np.uint32)
             t = O.freq_table_from_histogram(hist)
-            want = O.rans_encode_interleaved(sy, t)
+            try:
+                want = O.rans_encode_interleaved(sy, t)
+            except O.OracleError as e:          # a used symbol whose wrapped frequency is 0: the reference divides by zero
+                assert e.code == O.ERR_PANIC
+                try:
+                    api.rans_encode_interleaved(sy, hist)
+                    raise AssertionError("ReferencePanic expected")
+                except pkg.CodecError as ce:
+                    assert ce.kind == "ReferencePanic", ce.kind
+                continue
             got = api.rans_encode_interleaved(sy, hist)
             assert got == want, (n, kind)
             for m in sorted({n, n // 2, max(n - 1, 0), min(n, 5)}):

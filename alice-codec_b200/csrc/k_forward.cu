@@ -26,6 +26,12 @@
 #define ALICE_FWD_M 2   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
 #endif
 
+// 1: k_fwd_xy runs one colour channel per warp (grid.y = 3): a third of the lifting state per lane (205 -> ~100
+// registers for CDF 9/7), three times the warps, RGB rows read three times (from L2) and the colour transform repeated.
+// Emulator parity green; not yet measured on hardware, hence off.
+#ifndef ALICE_XY_SPLIT_CH
+#define ALICE_XY_SPLIT_CH 0
+#endif
 // experiment knob: unroll factor of the steady-state row-pair loop of k_fwd_xy (unset = the compiler's choice)
 #define ALICE_PRAGMA_(x) _Pragma(#x)
 #define ALICE_PRAGMA(x) ALICE_PRAGMA_(x)
@@ -97,9 +103,11 @@ ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, in
 
 // One column strip of one frame, rows [i0, i1) of the y-transformed output.  EDGE = false: the strip touches neither
 // the left nor the right image border, every access is in range and aligned.
-template <int WT, int M, bool EDGE>
+// NCH = 3: the warp transforms all three colour channels; NCH = 1: only channel c0 (a third of the lifting state per
+// lane, three times the warps — ALICE_XY_SPLIT_CH).
+template <int WT, int M, bool EDGE, int NCH>
 ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict__ out_t, size_t plane_sz, int w, int h,
-                          int pw, int p0, int i0, int i1, int lane, bool vec_ok) {
+                          int pw, int p0, int i0, int i1, int lane, bool vec_ok, int c0) {
     constexpr int NST = WaveletTraits<WT>::NST;
     constexpr int PXL = 2 * M;
     const int halfx = pw >> 1, halfy = (h + (h & 1)) >> 1;
@@ -109,7 +117,7 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     const int js = max(0, i0 - NST);
     const int je = min(halfy, i1 + NST);
 
-    FwdLift<WT, false> L[3][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
+    FwdLift<WT, false> L[NCH][PXL];  // per channel: columns [0,M) = low-x, [M,2M) = high-x
 
     auto load_pair = [&](int j, RowRaw<M> (&raw)[2]) {
 #pragma unroll
@@ -119,8 +127,8 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
         }
     };
     // colour transform + x lifting of one row: v[c][0..M) = low-x, v[c][M..2M) = high-x
-    auto row_x = [&](const RowRaw<M> &raw, int (&v)[3][PXL]) {
-        int e[3][M], o[3][M];
+    auto row_x = [&](const RowRaw<M> &raw, int (&v)[NCH][PXL]) {
+        int e[NCH][M], o[NCH][M];
 #pragma unroll
         for (int i = 0; i < PXL; i++) {
             const int r = (raw.w[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 0xff;
@@ -131,21 +139,26 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
             const int tt = bb + (co >> 1);
             const int cg = g - tt;
             const int yy = tt + (cg >> 1);
-            if (i & 1) { o[0][i >> 1] = yy; o[1][i >> 1] = co; o[2][i >> 1] = cg; }
-            else       { e[0][i >> 1] = yy; e[1][i >> 1] = co; e[2][i >> 1] = cg; }
+            if (NCH == 3) {
+                if (i & 1) { o[0][i >> 1] = yy; o[NCH - 2][i >> 1] = co; o[NCH - 1][i >> 1] = cg; }
+                else       { e[0][i >> 1] = yy; e[NCH - 2][i >> 1] = co; e[NCH - 1][i >> 1] = cg; }
+            } else {
+                const int one = c0 == 0 ? yy : (c0 == 1 ? co : cg);
+                if (i & 1) o[0][i >> 1] = one; else e[0][i >> 1] = one;
+            }
         }
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < NCH; c++) {
             fwd_lanes<WT, false, M, EDGE>(e[c], o[c], p0, halfx);
 #pragma unroll
             for (int i = 0; i < M; i++) { v[c][i] = e[c][i]; v[c][M + i] = o[c][i]; }
         }
     };
-    auto emit = [&](int jo, const int (&lo)[3][PXL], const int (&hi)[3][PXL]) {
+    auto emit = [&](int jo, const int (&lo)[NCH][PXL], const int (&hi)[NCH][PXL]) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int16_t *row_lo = out_t + c * plane_sz + (size_t)jo * pw;
-            int16_t *row_hi = out_t + c * plane_sz + (size_t)(halfy + jo) * pw;
+        for (int c = 0; c < NCH; c++) {
+            int16_t *row_lo = out_t + (c0 + c) * plane_sz + (size_t)jo * pw;
+            int16_t *row_hi = out_t + (c0 + c) * plane_sz + (size_t)(halfy + jo) * pw;
             store_group_i16<M, EDGE>(row_lo, &lo[c][0], p0, halfx, lane_ok);
             store_group_i16<M, EDGE>(row_lo + halfx, &lo[c][M], p0, halfx, lane_ok);
             store_group_i16<M, EDGE>(row_hi, &hi[c][0], p0, halfx, lane_ok);
@@ -160,12 +173,12 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     int k = 0, j = js;
     for (; j < j_main; j++, k++) {
         if (j + 1 < je) load_pair(j + 1, nxt);
-        int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];
+        int v0[NCH][PXL], v1[NCH][PXL], lo[NCH][PXL], hi[NCH][PXL];
         row_x(cur[0], v0);
         row_x(cur[1], v1);
         bool has = false;
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int c = 0; c < NCH; c++)
 #pragma unroll
             for (int i = 0; i < PXL; i++) has = L[c][i].push(v0[c][i], v1[c][i], k, j, lo[c][i], hi[c][i]);
         if (has && j - NST >= i0 && j - NST < i1) emit(j - NST, lo, hi);
@@ -175,11 +188,11 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     ALICE_XY_UNROLL_PRAGMA
     for (; j < je; j++, k++) {
         load_pair(min(j + 1, je - 1), nxt);
-        int v0[3][PXL], v1[3][PXL], lo[3][PXL], hi[3][PXL];
+        int v0[NCH][PXL], v1[NCH][PXL], lo[NCH][PXL], hi[NCH][PXL];
         row_x(cur[0], v0);
         row_x(cur[1], v1);
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int c = 0; c < NCH; c++)
 #pragma unroll
             for (int i = 0; i < PXL; i++) L[c][i].push_steady(v0[c][i], v1[c][i], lo[c][i], hi[c][i]);
         emit(j - NST, lo, hi);
@@ -188,10 +201,10 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     if (je == halfy && k > 0) {
 #pragma unroll
         for (int which = 0; which < NST; which++) {
-            int lo[3][PXL], hi[3][PXL];
+            int lo[NCH][PXL], hi[NCH][PXL];
             bool has = false;
 #pragma unroll
-            for (int c = 0; c < 3; c++)
+            for (int c = 0; c < NCH; c++)
 #pragma unroll
                 for (int i = 0; i < PXL; i++) has = L[c][i].flush(k, which, halfy, lo[c][i], hi[c][i]);
             const int jo = halfy - NST + which;
@@ -200,8 +213,8 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
     }
 }
 
-template <int WT, int M>
-__global__ void ALICE_LAUNCH_BOUNDS(128, (M == 1 ? 4 : (WT == WT_CDF97 ? 2 : 3)))
+template <int WT, int M, int NCH>
+__global__ void ALICE_LAUNCH_BOUNDS(128, (NCH == 1 ? 5 : (M == 1 ? 4 : (WT == WT_CDF97 ? 2 : 3))))
 k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, int h, int f, int pw, int ph,
          int n_strips, int n_segs, int seg_pairs, int vec_ok) {
     constexpr int HL = (WaveletTraits<WT>::NST + M - 1) / M;
@@ -222,8 +235,9 @@ k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, i
     int16_t *out_t = planes + (size_t)t * ph * pw;
     // interior strip: no lane owns pair 0 or pair halfx-1 (the mirrored ones), all 32 lanes read inside the row
     const bool interior = vec_ok && sx > 0 && (sx + 1) * VPAIRS + HL * M <= halfx - 1 && (pw == w) && ((pw & 3) == 0);  // rows 4-byte aligned
-    if (interior) fwd_xy_strip<WT, M, false>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, true);
-    else fwd_xy_strip<WT, M, true>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, vec_ok != 0);
+    const int c0 = NCH == 1 ? (int)blockIdx.y : 0;   // one channel per warp: the channel is the grid's y index
+    if (interior) fwd_xy_strip<WT, M, false, NCH>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, true, c0);
+    else fwd_xy_strip<WT, M, true, NCH>(frame, out_t, plane_sz, w, h, pw, p0, i0, i1, lane, vec_ok != 0, c0);
 }
 
 // ------------------------------------------------------------------------- k_fwd_t_quant
@@ -440,7 +454,12 @@ static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbo
     const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
     const int warps_per_block = ALICE_XY_WPB;
     dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
-    auto kxy = k_fwd_xy<WT, M>;
+#if ALICE_XY_SPLIT_CH
+    grid.y = 3;
+    auto kxy = k_fwd_xy<WT, M, 1>;
+#else
+    auto kxy = k_fwd_xy<WT, M, 3>;
+#endif
     ALICE_LAUNCH(kxy, grid, dim3(32 * warps_per_block), 0, st, d_rgb, d_planes, w, h, f, pw, ph, n_strips, n_segs,
                  seg_pairs, vec_ok);
 

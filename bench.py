@@ -159,6 +159,11 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--in-place", action="store_true",
+                    help="experiment: encode from and decode into the same RGB buffer (0.53 instead of 0.93 GB per chunk "
+                         "in flight, so more rANS streams run concurrently); the inputs are regenerated on the device "
+                         "inside the timed region at the start of every step")
+    ap.add_argument("--max-chunks", type=int, default=0, help="cap on chunks in flight per GPU (0 = the default cap)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--lib", default=None, help="experiment build of libalice_codec (debugging aid)")
     ap.add_argument("--e2e-only", action="store_true", help="skip the device-resident timed region (debug)")
@@ -208,15 +213,19 @@ def main():
     free_b, total_b = torch.cuda.mem_get_info()
     # per chunk in flight: RGB in + RGB out (bench buffers; the output buffer doubles as the chunk's symbol-plane
     # workspace, ALICE_BATCH_SHARED_WORKSPACE) + payload budget (1 B/px + 192 KiB) + tables
-    per_chunk = 2 * rgb_bytes + n_px + 3 * 65536 + 3 * (16384 + 256 * 16 + 1024)
+    per_chunk = (1 if args.in_place else 2) * rgb_bytes + n_px + 3 * 65536 + 3 * (16384 + 256 * 16 + 1024)
     fixed = 12 * n_px + (2 << 30)            # 4-byte scratch volume x 3 channels + head-room
-    B = args.chunks or max(1, min(176, int((free_b - fixed) // per_chunk)))
+    cap = args.max_chunks or (197 if args.in_place else 176)   # 197 = 592 concurrent decoder streams / 3
+    B = args.chunks or max(1, min(cap, int((free_b - fixed) // per_chunk)))
     d_in = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
-    d_out = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
-    for i, t in enumerate(d_in):
-        # chunk ids follow the round-robin sharding of alice_codec_b200.sharding: rank r holds chunks r, r+world, ...
-        api._chk(api.lib.alice_codec_synth_rgb_device(1, SEED + rank + i * world, W, H, F, C.c_void_p(t.data_ptr()),
-                                                      C.c_void_p(stream.cuda_stream)))
+    d_out = d_in if args.in_place else [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
+
+    def synth_inputs():
+        for i, t in enumerate(d_in):
+            # chunk ids follow the round-robin sharding of alice_codec_b200.sharding: rank r holds chunks r, r+world, ...
+            api._chk(api.lib.alice_codec_synth_rgb_device(1, SEED + rank + i * world, W, H, F, C.c_void_p(t.data_ptr()),
+                                                          C.c_void_p(stream.cuda_stream)))
+    synth_inputs()
     torch.cuda.synchronize()
     batch = pkg.ChunkBatch(args.quality, args.wavelet, W, H, F, B, stream=stream.cuda_stream, api=api,
                            shared_workspace=True)
@@ -225,6 +234,8 @@ def main():
     out_ptrs = [t.data_ptr() for t in d_out]
 
     def step():
+        if args.in_place:
+            synth_inputs()                         # the previous step decoded over the inputs
         batch.encode_device(in_ptrs, out_ptrs)     # symbol planes of chunk i live in its output buffer ...
         batch.decode_device(out_ptrs)              # ... until the decode back-end overwrites them with RGB
 
@@ -273,7 +284,7 @@ def main():
     # region).  Informational: the reference's decode of its own stream is not a reconstruction and the
     # CUDA path reproduces exactly that output, so a low figure here is the reference's, not a defect.
     psnr_db = None
-    if rank == 0:
+    if rank == 0 and not args.in_place:
         try:
             psnr_db = round(api.psnr_device(d_in[0].data_ptr(), d_out[0].data_ptr(), int(d_in[0].numel()),
                                             stream.cuda_stream), 3)
@@ -331,6 +342,9 @@ def main():
 
     # ---- e2e: the same metric through the host-buffer C-ABI call, copies inside the timed region
     e2e = None
+    if args.in_place and not args.no_e2e:
+        synth_inputs()                                  # the last step decoded over the inputs the e2e leg copies out
+        torch.cuda.synchronize()
     if not args.no_e2e:
         # The caller-side pattern for host buffers: T host threads, each driving its own ChunkBatch (own CUDA stream)
         # over its share of the chunks, so one batch's PCIe copies run under another batch's rANS kernels.
@@ -433,8 +447,9 @@ def main():
                 "config": {"workload": WORKLOAD, "chunks_per_gpu_per_step": B, "frames_per_step": frames_per_step,
                            "input": "G1 tri+hash volumes generated on the device, one seed per chunk",
                            "l2": "inputs (%.1f GB per step per GPU) are far larger than the 126 MB L2" % (B * rgb_bytes / 1e9),
-                           "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective"},
-                "e2e": e2e, "gpu_launches": args.steps * (5 * B + 4), "roofline": roofline, "roofline_by_kernel": by_kernel,
+                           "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective",
+                           **({"in_place": "inputs regenerated on the device inside every timed step"} if args.in_place else {})},
+                "e2e": e2e, "gpu_launches": args.steps * ((6 if args.in_place else 5) * B + 4), "roofline": roofline, "roofline_by_kernel": by_kernel,
                 "stages": stages,
                 "cpu_baseline": cpu, "clocks": sampler.summary(), "bit_exact_vs_oracle_digest": bit_exact,
                 "psnr_decoded_vs_input_db": psnr_db}

@@ -300,3 +300,16 @@ def test_determinism_and_idempotence(api):
     d1 = pkg.FrameDecoder(api=api).decode(ck)
     d2 = pkg.FrameDecoder(api=api).decode(ck)
     assert np.array_equal(d1, d2)
+
+
+@pytest.mark.xfail(strict=False, reason="experimental decoder table layout, off by default; first hardware exposure")
+def test_zz_experimental_rans_decode_split16_layout(api, monkeypatch):
+    """LAST on purpose.  The 16-bit split decoder tables (33 KB per stream, six streams per SM; selected at run time,
+    off by default until measured) must decode exactly like the default 8-byte entries.  Parity is proven in the
+    emulator tier; this is the hardware check, marked xfail(strict=False) so that it informs without gating."""
+    monkeypatch.setenv("ALICE_RANS_DEC_SPLIT16", "1")
+    parity.check_rans_api(api, np.random.default_rng(2), n=6000)
+    for wavelet in (0, 1, 2):
+        parity.check_encode_decode(api, O.G1, 260, 4, 64, 80, wavelet)
+        parity.check_encode_decode(api, O.G2, 124, 62, 8, 100, wavelet)
+    parity.check_decode_foreign_headers(api, np.random.default_rng(3))

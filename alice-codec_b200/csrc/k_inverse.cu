@@ -35,6 +35,15 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 // hand-off type between the t pass and the y/x pass: i32 in both variants (an i16 hand-off measured slower in
 // k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
 template <bool WIDE> struct Handoff { typedef int32_t T; };
+// 1: the narrow variant hands i16 from the t pass to the y/x pass (1.6 GB less traffic per 1080p x 64 chunk).  It
+// measured slower while k_inv_yx waited on every load; with the prefetching k_inv_yx the back-end is within 1.7x of its
+// DRAM floor and the question is open again.  Emulator parity green; not yet re-measured, hence off.
+#ifndef ALICE_HANDOFF_I16
+#define ALICE_HANDOFF_I16 0
+#endif
+#if ALICE_HANDOFF_I16
+template <> struct Handoff<false> { typedef int16_t T; };
+#endif
 
 // 1: k_inv_yx prefetches the next row pair, takes unchecked 8-byte loads on interior strips and runs the steady-state
 // lifting form after the warm-up.  Measured on B200 (1080p x 64, CDF 9/7, whole back-end): 1.600 -> 1.060 ms, decoded
@@ -265,7 +274,7 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
     // The row pair j + 1 is loaded before pair j is transformed (the kernel's dominant stall was long_scoreboard: every
     // iteration waited for its own loads), strips whose 32 lanes are all inside the row use plain 8-byte loads without
     // range or alignment tests, and after the warm-up the lifting state machine runs its branch-free steady form.
-    const bool fast_ld = M == 2 && sizeof(HT) == 4 && sx * VPAIRS - M >= 0 && sx * VPAIRS - M + 32 * M <= halfx &&
+    const bool fast_ld = M == 2 && sx * VPAIRS - M >= 0 && sx * VPAIRS - M + 32 * M <= halfx &&
                          (halfx & 1) == 0 && (pw & 1) == 0 && (reinterpret_cast<uintptr_t>(coef) & 7) == 0;
     auto load_rows = [&](int j, int (&lo)[3][PXL], int (&hi)[3][PXL]) {
 #pragma unroll
@@ -275,16 +284,27 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
             if (fast_ld) {
 #ifdef ALICE_EMUL
                 if (((reinterpret_cast<uintptr_t>(row_lo + p0) | reinterpret_cast<uintptr_t>(row_lo + halfx + p0) |
-                      reinterpret_cast<uintptr_t>(row_hi + p0) | reinterpret_cast<uintptr_t>(row_hi + halfx + p0)) & 7) != 0 ||
+                      reinterpret_cast<uintptr_t>(row_hi + p0) | reinterpret_cast<uintptr_t>(row_hi + halfx + p0)) & (2 * sizeof(HT) - 1)) != 0 ||
                     p0 < 0 || p0 + M > halfx || j < 0 || j >= halfy)
                     abort();   // the emulator does not fault on what the GPU would
 #endif
-                const int2 a = __ldg(reinterpret_cast<const int2 *>(row_lo + p0));
-                const int2 b = __ldg(reinterpret_cast<const int2 *>(row_lo + halfx + p0));
-                const int2 c2 = __ldg(reinterpret_cast<const int2 *>(row_hi + p0));
-                const int2 d = __ldg(reinterpret_cast<const int2 *>(row_hi + halfx + p0));
-                lo[c][0] = a.x; lo[c][1] = a.y; lo[c][PXL - 2] = b.x; lo[c][PXL - 1] = b.y;
-                hi[c][0] = c2.x; hi[c][1] = c2.y; hi[c][PXL - 2] = d.x; hi[c][PXL - 1] = d.y;
+                if (sizeof(HT) == 4) {
+                    const int2 a = __ldg(reinterpret_cast<const int2 *>(row_lo + p0));
+                    const int2 b = __ldg(reinterpret_cast<const int2 *>(row_lo + halfx + p0));
+                    const int2 c2 = __ldg(reinterpret_cast<const int2 *>(row_hi + p0));
+                    const int2 d = __ldg(reinterpret_cast<const int2 *>(row_hi + halfx + p0));
+                    lo[c][0] = a.x; lo[c][1] = a.y; lo[c][PXL - 2] = b.x; lo[c][PXL - 1] = b.y;
+                    hi[c][0] = c2.x; hi[c][1] = c2.y; hi[c][PXL - 2] = d.x; hi[c][PXL - 1] = d.y;
+                } else {                                   // i16 hand-off: two values per 4-byte load
+                    const uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(row_lo + p0));
+                    const uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(row_lo + halfx + p0));
+                    const uint32_t c2 = __ldg(reinterpret_cast<const uint32_t *>(row_hi + p0));
+                    const uint32_t d = __ldg(reinterpret_cast<const uint32_t *>(row_hi + halfx + p0));
+                    lo[c][0] = (int16_t)(a & 0xffff); lo[c][1] = (int)a >> 16;
+                    lo[c][PXL - 2] = (int16_t)(b & 0xffff); lo[c][PXL - 1] = (int)b >> 16;
+                    hi[c][0] = (int16_t)(c2 & 0xffff); hi[c][1] = (int)c2 >> 16;
+                    hi[c][PXL - 2] = (int16_t)(d & 0xffff); hi[c][PXL - 1] = (int)d >> 16;
+                }
             } else {
                 int t0[M], t1[M], t2[M], t3[M];
                 load_group_i32<M, HT>(row_lo, p0, halfx, t0);

@@ -18,7 +18,7 @@ struct EncodedChunk { Chunk c; };
 struct AliceBatch {
     Engine *eng = nullptr;
     uint8_t quality = 0, wavelet = 0;
-    std::vector<uint8_t *> stage_ptrs;
+    std::vector<uint8_t *> stage_ptrs, work_ptrs;
 };
 
 #define CU_CHECK_RC(expr)                                                                   \
@@ -930,16 +930,21 @@ int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, ui
     Engine *e = b->eng;
     if (n > e->cap_chunks()) { set_error(kErrBufferSize, "batch larger than capacity"); return kErrBufferSize; }
     const size_t bytes = (size_t)e->dims().n_pixels * 3;
+    // Shared-workspace batches keep the symbol planes of chunk i in the RGB staging buffer of chunk i - 1 (chunk 0: one
+    // spare buffer): the front-end of chunk i runs after that of chunk i - 1 has consumed its RGB, and a workspace that is
+    // not the chunk's own RGB lets the fused front-end kernel run (Engine::encode_device).
+    const bool shared = e->shared_workspace();
     b->stage_ptrs.resize(n);
+    b->work_ptrs.resize(n);
     for (uint32_t i = 0; i < n; i++) {
-        uint8_t *s = e->rgb_stage(i);
-        if (!s) return kErrCuda;
+        uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
+        if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
         b->stage_ptrs[i] = s;
+        b->work_ptrs[i] = shared ? e->rgb_stage(i) : nullptr;
         CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
     }
-    // shared-workspace batches keep each chunk's symbol planes in its RGB staging buffer
     int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr,
-                              e->shared_workspace() ? b->stage_ptrs.data() : nullptr);
+                              shared ? b->work_ptrs.data() : nullptr);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++) {
         out_chunks[i] = alice_codec_batch_get_chunk(b, i);

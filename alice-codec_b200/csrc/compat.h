@@ -51,6 +51,67 @@ template <int OFF> __device__ __forceinline__ uint32_t smem_ld_u32(smem_addr_t a
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (cp.async.bulk, the 1-D form of the TMA engine) completing on an mbarrier: the fused
+// wavelet kernels stage their input rows in shared memory several row pairs ahead without spending registers on
+// loads in flight.  One elected thread arms the barrier with the byte count of a stage (mbar_arrive_expect_tx), any
+// threads issue the copies (bulk_copy_g2s), every consumer waits on the phase parity (mbar_wait).
+// The emulator has no asynchronous proxy: the shim copies at issue time and models the barrier's phase/transaction
+// accounting, so the kernels' index and phase logic is exercised on the CPU; ordering and latency are not.
+#ifdef ALICE_EMUL
+struct mbar_t { unsigned completed; int pending, count; long long tx; };
+inline void mbar_emul_check(mbar_t *b) {
+    if (b->pending == 0 && b->tx == 0) { b->completed++; b->pending = b->count; }
+}
+inline void mbar_init(mbar_t *b, int count) { b->completed = 0; b->pending = b->count = count; b->tx = 0; }
+inline void mbar_fence_init() {}
+inline void mbar_arrive_expect_tx(mbar_t *b, unsigned bytes) { b->tx += bytes; b->pending--; mbar_emul_check(b); }
+inline void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, mbar_t *b) {
+    if (((uintptr_t)dst_smem & 15) || ((uintptr_t)src_gmem & 15) || (bytes & 15)) {
+        fprintf(stderr, "cuda_emul: cp.async.bulk needs 16-byte aligned addresses and size\n");
+        abort();
+    }
+    memcpy(dst_smem, src_gmem, bytes);
+    b->tx -= bytes;
+    mbar_emul_check(b);
+}
+inline void mbar_wait(mbar_t *b, unsigned parity) {
+    while ((b->completed & 1u) == (parity & 1u)) ::emul::yield();   // the phase with this parity has not completed yet
+}
+#else
+typedef unsigned long long mbar_t;
+__device__ __forceinline__ void mbar_init(mbar_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {   // make the initialised barriers visible to the async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(mbar_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, mbar_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(mbar_t *b, unsigned parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 namespace alice {
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 constexpr unsigned kFullMask = 0xffffffffu;

@@ -221,6 +221,8 @@ Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStr
     a = a && dev_alloc(d_payload_, S * pay_cap_, dev_bytes_);
     a = a && dev_alloc(d_enc_jobs_, S * sizeof(RansEncJob), dev_bytes_);
     a = a && dev_alloc(d_dec_jobs_, S * sizeof(RansDecJob), dev_bytes_);
+    a = a && dev_alloc(d_fwd_jobs_, (size_t)cap_ * sizeof(FwdFusedJob), dev_bytes_);
+    a = a && cudaMallocHost((void **)&h_fwd_jobs_, (size_t)cap_ * sizeof(FwdFusedJob)) == cudaSuccess;
     a = a && dev_alloc(d_results_, S * 2 * sizeof(unsigned long long), dev_bytes_);
     a = a && cudaMallocHost((void **)&h_results_, S * 2 * sizeof(unsigned long long)) == cudaSuccess;
     a = a && cudaMallocHost((void **)&h_hist_, S * 256 * sizeof(unsigned)) == cudaSuccess;
@@ -249,6 +251,8 @@ Engine::~Engine() {
     if (h_hist_) cudaFreeHost(h_hist_);
     if (h_enc_jobs_) cudaFreeHost(h_enc_jobs_);
     if (h_dec_jobs_) cudaFreeHost(h_dec_jobs_);
+    if (h_fwd_jobs_) cudaFreeHost(h_fwd_jobs_);
+    cudaFree(d_fwd_jobs_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     if (st_ && own_stream_) cudaStreamDestroy(st_);
     cudaGetLastError();
@@ -344,10 +348,38 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     last_n = n;
     CU_TRY(cudaMemsetAsync(d_hist_, 0, (size_t)n * 3 * 256 * sizeof(unsigned), st_));
     CU_TRY(cudaEventRecord(ev_[0], st_));
+    // Front-end.  64-frame chunks of even height and a width that is a multiple of 16 take the fused kernel
+    // (k_fwd_fused.cu), which reads RGB and writes symbols in the same launch: a chunk whose symbol workspace overlaps the
+    // RGB of a chunk of the same launch cannot use it.  Engine-owned symbol planes: one launch for the whole batch.
+    // Caller-provided workspaces (shared-workspace batches): one launch per chunk, in index order, so workspace i may be
+    // the RGB buffer of any chunk j < i (already consumed); a workspace that overlaps its own chunk's RGB falls back to
+    // the two-kernel path, which finishes reading the RGB before the first symbol is written.
+    auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
+    bool all_fused = true;
     for (uint32_t c = 0; c < n; c++)
-        forward_frontend(wavelet, d_rgb[c], reinterpret_cast<int16_t *>(d_scratch_), sym_ptr_[c],
-                         d_hist_ + (size_t)c * 3 * 256, (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph,
-                         (int)d_.pf, step, c == 0 ? d_coef_dump : nullptr, st_);
+        all_fused = all_fused && forward_fused_eligible(d_rgb[c], (int)d_.w, (int)d_.h, (int)d_.f) &&
+                    (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0;
+    if (all_fused) {
+        for (uint32_t c = 0; c < n; c++)
+            h_fwd_jobs_[c] = FwdFusedJob{d_rgb[c], sym_ptr_[c], d_hist_ + (size_t)c * 3 * 256, c == 0 ? d_coef_dump : nullptr};
+        CU_TRY(cudaMemcpyAsync(d_fwd_jobs_, h_fwd_jobs_, n * sizeof(FwdFusedJob), cudaMemcpyHostToDevice, st_));
+    }
+    const int n_sms = device_sm_count();
+    for (uint32_t c = 0; c < n;) {
+        if (!all_fused || (shared_ws_ && overlaps(sym_ptr_[c], 3 * N, d_rgb[c], 3 * (size_t)d_.n_pixels))) {
+            forward_frontend(wavelet, d_rgb[c], reinterpret_cast<int16_t *>(d_scratch_), sym_ptr_[c],
+                             d_hist_ + (size_t)c * 3 * 256, (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph,
+                             (int)d_.pf, step, c == 0 ? d_coef_dump : nullptr, st_);
+            c++;
+            continue;
+        }
+        // a run of chunks for one launch: the whole rest of an engine-owned batch, a single chunk otherwise (or chunk 0
+        // alone when its coefficients are dumped for the parity tests)
+        uint32_t m = (shared_ws_ || (c == 0 && d_coef_dump)) ? 1 : n - c;
+        forward_frontend_fused(wavelet, d_fwd_jobs_ + c, (int)m, c == 0 && d_coef_dump != nullptr,
+                               d_hist_ + (size_t)c * 3 * 256, (int)d_.w, (int)d_.h, step, n_sms, st_);
+        c += m;
+    }
     CU_TRY(cudaEventRecord(ev_[1], st_));
     build_tables(d_hist_, (int)n * 3, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
     CU_TRY(cudaEventRecord(ev_[2], st_));

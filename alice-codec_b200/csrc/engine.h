@@ -135,6 +135,7 @@ private:
     uint8_t *d_payload_ = nullptr;    // [cap*3][pay_cap]
     RansEncJob *d_enc_jobs_ = nullptr;
     RansDecJob *d_dec_jobs_ = nullptr;
+    FwdFusedJob *d_fwd_jobs_ = nullptr, *h_fwd_jobs_ = nullptr;   // per chunk: RGB, symbols, histogram (fused front-end)
     unsigned long long *d_results_ = nullptr;  // [cap*3][2]
     std::vector<uint8_t *> rgb_stage_;
     std::vector<uint8_t *> overflow_bufs_;     // per stream, full-size retry buffers (rare)

@@ -21,25 +21,14 @@
 // All arithmetic is 32-bit: for u8 input every product (a+b)*c stays below 2^31.
 #include "kernels.h"
 #include "lifting.cuh"
+#include "quant.cuh"
 
 #ifndef ALICE_FWD_M
 #define ALICE_FWD_M 2   // horizontal pairs per lane in k_fwd_xy (1: 96 registers, 2: 150-205 registers)
 #endif
 
-// 1: k_fwd_xy runs one colour channel per warp (grid.y = 3): a third of the lifting state per lane (205 -> ~100
-// registers for CDF 9/7), three times the warps, RGB rows read three times (from L2) and the colour transform repeated.
-// Emulator parity green; not yet measured on hardware, hence off.
-#ifndef ALICE_XY_SPLIT_CH
-#define ALICE_XY_SPLIT_CH 0
-#endif
-// experiment knob: unroll factor of the steady-state row-pair loop of k_fwd_xy (unset = the compiler's choice)
-#define ALICE_PRAGMA_(x) _Pragma(#x)
-#define ALICE_PRAGMA(x) ALICE_PRAGMA_(x)
-#ifdef ALICE_XY_UNROLL
-#define ALICE_XY_UNROLL_PRAGMA ALICE_PRAGMA(unroll ALICE_XY_UNROLL)
-#else
-#define ALICE_XY_UNROLL_PRAGMA
-#endif
+// (Measured and dropped, profiles/r02_switches.md: one colour channel per warp -- 96 instead of 205 registers, RGB read
+//  three times -- 1.173 ms against 1.110 ms for the whole front-end; unrolling the row-pair loop by 2 / 4: 1.31 / 1.82 ms.)
 
 namespace alice {
 
@@ -57,11 +46,7 @@ ALICE_D void load_row_raw(const uint8_t *__restrict__ row, int x0, int w, bool v
         if (NB % 4 == 0) {
             const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x0 * 3);
 #pragma unroll
-#ifdef ALICE_XY_PLAIN_LD
-            for (int i = 0; i < NW; i++) raw.w[i] = p[i];
-#else
             for (int i = 0; i < NW; i++) raw.w[i] = __ldg(p + i);
-#endif
         } else {                         // 6 bytes at a 2-byte aligned address (x0 is even)
             const uint16_t *p = reinterpret_cast<const uint16_t *>(row + (size_t)x0 * 3);
             raw.w[0] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 16);
@@ -103,8 +88,7 @@ ALICE_D void store_group_i16(int16_t *__restrict__ dst, const int *v, int xp, in
 
 // One column strip of one frame, rows [i0, i1) of the y-transformed output.  EDGE = false: the strip touches neither
 // the left nor the right image border, every access is in range and aligned.
-// NCH = 3: the warp transforms all three colour channels; NCH = 1: only channel c0 (a third of the lifting state per
-// lane, three times the warps — ALICE_XY_SPLIT_CH).
+// NCH = 3: the warp transforms all three colour channels.
 template <int WT, int M, bool EDGE, int NCH>
 ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict__ out_t, size_t plane_sz, int w, int h,
                           int pw, int p0, int i0, int i1, int lane, bool vec_ok, int c0) {
@@ -185,7 +169,6 @@ ALICE_D void fwd_xy_strip(const uint8_t *__restrict__ frame, int16_t *__restrict
         cur[0] = nxt[0]; cur[1] = nxt[1];
     }
     // steady state: the next row pair is already in flight while this one is transformed
-    ALICE_XY_UNROLL_PRAGMA
     for (; j < je; j++, k++) {
         load_pair(min(j + 1, je - 1), nxt);
         int v0[NCH][PXL], v1[NCH][PXL], lo[NCH][PXL], hi[NCH][PXL];
@@ -241,34 +224,14 @@ k_fwd_xy(const uint8_t *__restrict__ rgb, int16_t *__restrict__ planes, int w, i
 }
 
 // ------------------------------------------------------------------------- k_fwd_t_quant
-struct QuantDev {
-    int step, dz, half_dz;
-    uint32_t magic;  // ceil(2^32 / step) for step >= 2
-};
-
-ALICE_D uint32_t quant_symbol(int v, const QuantDev &q) {
-    // Quantizer::quantize (quant.rs:89-97) with dead_zone == step >= 1, then to_symbols (quant.rs:555-560),
-    // without branches: for |v| < step the numerator |v| - step/2 is below step, so clamping it at 0 gives the
-    // dead zone; the symbol 2q-1 (v > 0) / 2q (v < 0) is max(2q - 1 - (v >> 31), 0) because q == 0 when v == 0.
-    const int a = v < 0 ? -v : v;
-    const int n = max(a - q.half_dz, 0);
-    const uint32_t qa = q.step == 1 ? (uint32_t)n : __umulhi((uint32_t)n, q.magic);   // exact: n < 2^26, magic = ceil(2^32/step)
-    const int s = max((int)(2u * qa) - 1 - (v >> 31), 0);
-    return (uint32_t)s & 0xffu;
-}
-
 #ifndef ALICE_T_MINBLOCKS
 #define ALICE_T_MINBLOCKS 4
 #endif
-// 1: the compile-time-depth variant of k_fwd_t_quant runs a rolled, software-pipelined steady-state loop (31 KB of
-// code) instead of the fully unrolled one (122 KB, four times the instruction cache).  Measured on B200 (1080p x 64,
-// CDF 9/7, whole front-end): unrolled 1.209 ms, rolled 1.122 ms, rolled with three blocks per SM (85 registers, no
-// spills) 1.106 ms (profiles/r01_ab_frontend.jsonl).
-#ifndef ALICE_T_ROLLED
-#define ALICE_T_ROLLED 1
-#endif
+// The compile-time-depth variant (PF = 64) runs a rolled, software-pipelined steady-state loop (31 KB of code); the
+// fully unrolled form (122 KB, four times the instruction cache) measured 1.209 ms against 1.106 ms for the whole
+// front-end (profiles/r01_ab_frontend.jsonl) and was dropped.
 template <int WT, int VEC, int PF>
-__global__ void ALICE_LAUNCH_BOUNDS(256, (PF != 0 && ALICE_T_ROLLED) ? 3 : ALICE_T_MINBLOCKS)
+__global__ void ALICE_LAUNCH_BOUNDS(256, PF != 0 ? 3 : ALICE_T_MINBLOCKS)
 k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols, unsigned *__restrict__ hist,
               int pw, int ph, int f, int pf, QuantDev q, int32_t *__restrict__ coef_dump) {
     constexpr int NST = WaveletTraits<WT>::NST;
@@ -341,7 +304,7 @@ k_fwd_t_quant(const int16_t *__restrict__ planes, uint8_t *__restrict__ symbols,
                 o[2 * i] = (int16_t)(r.b[i] & 0xffff); o[2 * i + 1] = (int)r.b[i] >> 16;
             }
         };
-        if (PF != 0 && ALICE_T_ROLLED) {
+        if (PF != 0) {
             // Compile-time depth: a short unrolled prologue (warm-up and the mirrored left edge), a ROLLED
             // steady-state loop with the rows of the next two pairs in flight, and three peeled pairs at the end
             // (the last load is the only one that may need the frame clamp).  The fully unrolled form of this loop
@@ -454,20 +417,11 @@ static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbo
     const int vec_ok = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rgb) & 3) == 0);
     const int warps_per_block = ALICE_XY_WPB;
     dim3 grid((unsigned)((n_warps + warps_per_block - 1) / warps_per_block));
-#if ALICE_XY_SPLIT_CH
-    grid.y = 3;
-    auto kxy = k_fwd_xy<WT, M, 1>;
-#else
     auto kxy = k_fwd_xy<WT, M, 3>;
-#endif
     ALICE_LAUNCH(kxy, grid, dim3(32 * warps_per_block), 0, st, d_rgb, d_planes, w, h, f, pw, ph, n_strips, n_segs,
                  seg_pairs, vec_ok);
 
-    QuantDev q;
-    q.step = step;
-    q.dz = step;
-    q.half_dz = step / 2;
-    q.magic = step >= 2 ? (uint32_t)((((uint64_t)1 << 32) + step - 1) / step) : 0;
+    const QuantDev q = make_quant_dev(step);
     const size_t frame_sz = (size_t)pw * ph;
     const int vec = (pw % 4 == 0) ? 4 : 2;
     const long long items = frame_sz / vec;

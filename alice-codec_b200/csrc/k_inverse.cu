@@ -32,30 +32,13 @@ ALICE_D int sym_to_coef(uint32_t s, int step) {
 
 // WIDE = true : the reference's wrapping i32 arithmetic with the i64 lifting product, i32 hand-off (any header).
 // WIDE = false: 32-bit products and an i16 hand-off, exact while 128 * |quant_step| <= kNarrowMaxCoef (see launcher).
-// hand-off type between the t pass and the y/x pass: i32 in both variants (an i16 hand-off measured slower in
-// k_inv_yx: 2.62 ms vs 1.65 ms per 1080p x 64 chunk, although it halves the traffic)
+// hand-off type between the t pass and the y/x pass: i32 in both variants.  An i16 hand-off halves the traffic but
+// measured slower twice: 2.62 vs 1.65 ms per 1080p x 64 chunk in round 1 and, with the prefetching k_inv_yx,
+// 1.549 vs 1.058 ms in round 2 (profiles/r02_switches.md); it was dropped.
 template <bool WIDE> struct Handoff { typedef int32_t T; };
-// 1: the narrow variant hands i16 from the t pass to the y/x pass (1.6 GB less traffic per 1080p x 64 chunk).  It
-// measured slower while k_inv_yx waited on every load; with the prefetching k_inv_yx the back-end is within 1.7x of its
-// DRAM floor and the question is open again.  Emulator parity green; not yet re-measured, hence off.
-#ifndef ALICE_HANDOFF_I16
-#define ALICE_HANDOFF_I16 0
-#endif
-#if ALICE_HANDOFF_I16
-template <> struct Handoff<false> { typedef int16_t T; };
-#endif
-
-// 1: k_inv_yx prefetches the next row pair, takes unchecked 8-byte loads on interior strips and runs the steady-state
-// lifting form after the warm-up.  Measured on B200 (1080p x 64, CDF 9/7, whole back-end): 1.600 -> 1.060 ms, decoded
-// RGB equal to the oracle digest of BASELINE config 2 (profiles/r01_ab_backend.jsonl).
-#ifndef ALICE_YX_PREFETCH
-#define ALICE_YX_PREFETCH 1
-#endif
-// 1: 64-frame chunks use the rolled, software-pipelined compile-time-depth variant of k_inv_t (see the kernel).
-// Measured on B200 (1080p x 64, CDF 9/7, whole back-end): 1.666 -> 1.600 ms (profiles/r01_ab_backend.jsonl).
-#ifndef ALICE_INV_T_ROLLED
-#define ALICE_INV_T_ROLLED 1
-#endif
+// k_inv_yx prefetches the next row pair, takes unchecked 8-byte loads on interior strips and runs the steady-state lifting
+// form after the warm-up (1.600 -> 1.060 ms for the whole back-end, profiles/r01_ab_backend.jsonl); 64-frame chunks use the
+// rolled, software-pipelined compile-time-depth variant of k_inv_t (1.666 -> 1.600 ms).
 
 template <int WT, int VEC, int PF, bool WIDE>
 __global__ void ALICE_LAUNCH_BOUNDS(256, (PF ? 3 : 4))
@@ -270,7 +253,6 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
         }
     };
 
-#if ALICE_YX_PREFETCH
     // The row pair j + 1 is loaded before pair j is transformed (the kernel's dominant stall was long_scoreboard: every
     // iteration waited for its own loads), strips whose 32 lanes are all inside the row use plain 8-byte loads without
     // range or alignment tests, and after the warm-up the lifting state machine runs its branch-free steady form.
@@ -288,22 +270,13 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
                     p0 < 0 || p0 + M > halfx || j < 0 || j >= halfy)
                     abort();   // the emulator does not fault on what the GPU would
 #endif
-                if (sizeof(HT) == 4) {
+                {
                     const int2 a = __ldg(reinterpret_cast<const int2 *>(row_lo + p0));
                     const int2 b = __ldg(reinterpret_cast<const int2 *>(row_lo + halfx + p0));
                     const int2 c2 = __ldg(reinterpret_cast<const int2 *>(row_hi + p0));
                     const int2 d = __ldg(reinterpret_cast<const int2 *>(row_hi + halfx + p0));
                     lo[c][0] = a.x; lo[c][1] = a.y; lo[c][PXL - 2] = b.x; lo[c][PXL - 1] = b.y;
                     hi[c][0] = c2.x; hi[c][1] = c2.y; hi[c][PXL - 2] = d.x; hi[c][PXL - 1] = d.y;
-                } else {                                   // i16 hand-off: two values per 4-byte load
-                    const uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(row_lo + p0));
-                    const uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(row_lo + halfx + p0));
-                    const uint32_t c2 = __ldg(reinterpret_cast<const uint32_t *>(row_hi + p0));
-                    const uint32_t d = __ldg(reinterpret_cast<const uint32_t *>(row_hi + halfx + p0));
-                    lo[c][0] = (int16_t)(a & 0xffff); lo[c][1] = (int)a >> 16;
-                    lo[c][PXL - 2] = (int16_t)(b & 0xffff); lo[c][PXL - 1] = (int)b >> 16;
-                    hi[c][0] = (int16_t)(c2 & 0xffff); hi[c][1] = (int)c2 >> 16;
-                    hi[c][PXL - 2] = (int16_t)(d & 0xffff); hi[c][PXL - 1] = (int)d >> 16;
                 }
             } else {
                 int t0[M], t1[M], t2[M], t3[M];
@@ -353,31 +326,6 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
         emit_pair(j - NST, ev, od);
         rotate();
     }
-#else
-    int k = 0;
-    for (int j = js; j < je; j++, k++) {
-        int ev[3][PXL], od[3][PXL];
-        bool has = false;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const HT *row_lo = in_t + c * plane_sz + (size_t)j * pw;
-            const HT *row_hi = in_t + c * plane_sz + (size_t)(halfy + j) * pw;
-            int lo[PXL], hi[PXL];
-            load_group_i32<M, HT>(row_lo, p0, halfx, &lo[0]);
-            load_group_i32<M, HT>(row_lo + halfx, p0, halfx, &lo[M]);
-            load_group_i32<M, HT>(row_hi, p0, halfx, &hi[0]);
-            load_group_i32<M, HT>(row_hi + halfx, p0, halfx, &hi[M]);
-#pragma unroll
-            for (int i = 0; i < PXL; i++) has = L[c][i].push(lo[i], hi[i], k, j, ev[c][i], od[c][i]);
-        }
-        if (has) {
-            const int jo = j - NST;
-            const bool active = jo >= i0 && jo < i1;
-            emit_row(2 * jo, active, ev);
-            emit_row(2 * jo + 1, active, od);
-        }
-    }
-#endif
     if (je == halfy) {
 #pragma unroll
         for (int which = 0; which < NST; which++) {
@@ -416,7 +364,7 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
         const dim3 tgrid(gx, 1, 3), tblock(256);
         // (a FULLY unrolled PF = 64 instantiation spilled 1.4-1.9 KB per thread and measured 2.3x slower than the
         //  runtime loop; the rolled compile-time-depth form is 4 % faster than the runtime loop on the whole back-end)
-        if (vec == 4 && pf == 64 && ALICE_INV_T_ROLLED) {
+        if (vec == 4 && pf == 64) {
             auto kt = k_inv_t<WT, 4, 64, WIDE>;
             ALICE_LAUNCH(kt, tgrid, tblock, 0, st, d_symbols, d_coef, pw, ph, f, pf, steps[0], steps[1], steps[2]);
         } else if (vec == 4) {

@@ -172,9 +172,37 @@ template <class K> static void ensure_dyn_smem(K kernel, int bytes, unsigned lon
     done_mask |= bit;
 }
 #endif
-// single-warp blocks when the launch alone gives every warp scheduler of the GPU a stream, else four warps per block
+// Block shape per launch.  The hardware places the warps of one block on the four warp schedulers of an SM in turn,
+// but it places single-warp blocks without regard to the scheduler: at six single-warp blocks per SM some schedulers
+// host two streams and some one, and the launch lasts as long as its slowest stream (profiles/r02_rans_occupancy.md).
+//   * more than four streams per SM: four-warp blocks, two (or three) blocks per SM = the same number of streams on
+//     every scheduler;
+//   * between two and four streams per SM: single-warp blocks (one per scheduler; 6-11 % faster per stream than the
+//     four-warp form in round 1);
+//   * fewer: four-warp blocks, so that the streams of several batches in flight spread over the schedulers.
+int device_sm_count() {
+#ifdef ALICE_EMUL
+    return kNumSMs;
+#else
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &c = cached[dev & 63];
+    if (c == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = kNumSMs; }
+        c = v;
+    }
+    return c;
+#endif
+}
 template <class F> static void launch_lanes(int n_streams, F f) {
-    if (n_streams >= 2 * kNumSMs) f(IntC<1>());
+    const int sms = device_sm_count();
+    if (const char *e = getenv("ALICE_RANS_FORCE_LPB")) {   // measurement hook (tools/rans_occupancy.py), removed once decided
+        if (e[0] == '1') return f(IntC<1>());
+        if (e[0] == '4') return f(IntC<4>());
+    }
+    if (n_streams >= 2 * sms && n_streams <= 4 * sms) f(IntC<1>());
     else f(IntC<4>());
 }
 
@@ -403,10 +431,13 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
         // launches) measured up to 2x slower; a four-warp decode block (195 KB) is exclusive anyway
         // (single-warp blocks padded to four per SM measured slightly worse under three concurrent batches:
         //  encode 2.8-2.95 s, decode 3.8-4.3 s vs 2.5-2.9 s and 4.04 s)
-        const int smem = LPB == 1 ? kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024);
+        // (small launches: a four-warp block asks for more than half an SM's shared memory so that the blocks of
+        //  concurrent launches do not stack on one SM; machine-filling launches take what they need: 72 KB per block)
+        const int smem = LPB == 1 ? kEncSmemPerWarp
+                                  : (n_streams > 4 * device_sm_count() ? LPB * kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024));
 #ifndef ALICE_EMUL
         static unsigned long long attr_done = 0;
-        ensure_dyn_smem(k_rans_encode<LPB>, smem, attr_done);
+        ensure_dyn_smem(k_rans_encode<LPB>, std::max(LPB * kEncSmemPerWarp, 116 * 1024), attr_done);
 #endif
         auto k = k_rans_encode<LPB>;
         ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);
@@ -414,19 +445,20 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
 }
 
 // --------------------------------------------------------------------------------- decode
-constexpr int kDecBlock = 256;                   // symbols per fast block (one 8-byte store per lane)
-constexpr int kWinPos = 1024;                    // byte positions held by the window ring
+constexpr int kDecBlock = 128;                   // symbols per fast block (one 4-byte store per lane)
+constexpr int kWinPos = 512;                     // byte positions held by the window ring
 constexpr int kWinMirror = 2 * kDecBlock + 16;   // positions mirrored past the end: a block reads linearly
-constexpr int kWinFill = 256;                    // bytes converted per refill (8 per lane)
-constexpr bool kDecSplit16Default = false;       // see kDecSmemBytes16
-// (48.9 KB per block in total, so four decode blocks fit the 227 KB of an SM: 592 concurrent streams)
+constexpr int kWinFill = 128;                    // bytes converted per refill (4 per lane)
 // window entry of position p: {bytes p..p+3, bytes p+4..p+7} as two big-endian words; 8 bytes per position makes
-// the renormalisation shift (8 bits per byte) equal to the address increment
-constexpr int kDecSmemBytes = kDecLutEntries * 8 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
-// SPLIT16 layout: {freq} and {slot - cum} as two u16 tables (16 KB instead of 32 KB; the two 2-byte loads zero-extend
-// for free, so the dependent chain LDS -> IMAD is unchanged): 33.3 KB per stream, six streams per SM instead of four.
-// Off by default until measured (ALICE_RANS_DEC_SPLIT16=1 selects it at run time).
-constexpr int kDecSmemBytes16 = kDecLutEntries * 4 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
+// the renormalisation shift (8 bits per byte) equal to the address increment.
+// Tables: {freq} and {slot - cum} as two u16 arrays (the two 2-byte loads zero-extend for free, so the dependent
+// chain LDS -> IMAD is that of one 8-byte entry).  26.4 KB per stream: eight streams per SM = two per warp scheduler.
+// Measured (profiles/r02_rans_occupancy.md): one stream per scheduler decodes 33-36 Msym/s, two sharing a scheduler
+// 28.8 Msym/s each (the step is latency bound, so the second stream is almost free); the 8-byte-entry layout of round 1
+// (48.9 KB, four streams per SM, 36.2 Msym/s per lane) gave 145 Msym/s per SM against 173+ for this one.
+constexpr int kDecSmemBytes = kDecLutEntries * 4 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
+static_assert(kDecSmemBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
+static_assert(kWinPos >= 2 * kDecBlock + 12 + kWinFill + 16, "a refill must not overwrite unread positions");
 
 struct DecState {
     uint32_t x;
@@ -435,15 +467,11 @@ struct DecState {
 };
 
 // generic step (rans.rs:351-371 literally), reading stream bytes from global memory
-template <bool SPLIT16>
 ALICE_D uint32_t dec_step_generic(DecState &s, const void *tab, const uint8_t *symt, uint32_t wide_sym,
                                   uint32_t wide_freq) {
     const uint32_t slot = s.x & (kProbScale - 1);
-    uint2 e;
-    if (SPLIT16) {
-        const uint16_t *f16 = reinterpret_cast<const uint16_t *>(tab);
-        e = make_uint2(f16[slot], f16[kDecLutEntries + slot]);
-    } else e = reinterpret_cast<const uint2 *>(tab)[slot];
+    const uint16_t *f16 = reinterpret_cast<const uint16_t *>(tab);
+    const uint2 e = make_uint2(f16[slot], f16[kDecLutEntries + slot]);
     const uint32_t sym = symt[slot];
     const uint32_t f = (sym == wide_sym) ? wide_freq : e.x;
     s.x = f * (s.x >> kProbBits) + e.y;          // low 32 bits of the reference's u64 expression
@@ -454,19 +482,18 @@ ALICE_D uint32_t dec_step_generic(DecState &s, const void *tab, const uint8_t *s
     return sym;
 }
 
-template <int LPB, bool SPLIT16>
+template <int LPB>
 __global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
               const DecAux *__restrict__ aux_all, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
     const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
     if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
-    constexpr int kTabBytes = SPLIT16 ? kDecLutEntries * 4 : kDecLutEntries * 8;
-    constexpr int SH = SPLIT16 ? 1 : 3;              // log2 of the table stride in bytes: slot << SH addresses the table(s)
-    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * (SPLIT16 ? kDecSmemBytes16 : kDecSmemBytes);
-    uint2 *ent = reinterpret_cast<uint2 *>(smem);                               // slot -> {freq, slot - cum}
-    uint16_t *f16 = reinterpret_cast<uint16_t *>(smem);                         // SPLIT16: slot -> freq ...
-    uint16_t *b16 = f16 + kDecLutEntries;                                       //          ... and slot -> slot - cum
+    constexpr int kTabBytes = kDecLutEntries * 4;
+    constexpr int SH = 1;                            // log2 of the table stride in bytes: slot << SH addresses the tables
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kDecSmemBytes;
+    uint16_t *f16 = reinterpret_cast<uint16_t *>(smem);                         // slot -> freq ...
+    uint16_t *b16 = f16 + kDecLutEntries;                                       // ... and slot -> slot - cum
     uint2 *win = reinterpret_cast<uint2 *>(smem + kTabBytes);                   // position -> next 8 bytes, big-endian
     uint8_t *symt = smem + kTabBytes + (kWinPos + kWinMirror) * 8;              // slot -> symbol
     uint16_t *slots = reinterpret_cast<uint16_t *>(symt + kDecLutEntries);      // slots decoded in this block
@@ -476,8 +503,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         const uint32_t *src = lut_all + (size_t)stream * kDecLutEntries;
         for (int i = lane; i < kDecLutEntries; i += 32) {
             const uint32_t p = src[i];
-            if (SPLIT16) { f16[i] = (uint16_t)(((p >> 8) & 0xfffu) + 1u); b16[i] = (uint16_t)(p >> 20); }
-            else ent[i] = make_uint2(((p >> 8) & 0xfffu) + 1u, p >> 20);
+            f16[i] = (uint16_t)(((p >> 8) & 0xfffu) + 1u);
+            b16[i] = (uint16_t)(p >> 20);
             symt[i] = (uint8_t)p;
         }
     }
@@ -510,7 +537,7 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
     auto careful = [&](unsigned long long upto) {   // generic steps for symbols [i, upto); true if the rest was filled
         for (; i < upto; i++) {
             const uint32_t xb = s.x;
-            const uint32_t sy = dec_step_generic<SPLIT16>(s, smem, symt, aux.wide_sym, aux.wide_freq);
+            const uint32_t sy = dec_step_generic(s, smem, symt, aux.wide_sym, aux.wide_freq);
             if (lane0) out[i] = (uint8_t)sy;
             if (s.pos >= s.len && s.x == xb) {
                 // exhausted stream and a fixed point of the state map: every further symbol is `sy`
@@ -543,22 +570,17 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         while (filled < o + 2ull * kDecBlock + 12) {
             __syncwarp();
             {
-                const unsigned long long base = filled + 8ull * lane;
-                uint32_t d[4];
-                if (base < end_off) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base));
-                    d[0] = v.x; d[1] = v.y;
-                } else { d[0] = d[1] = 0; }
-                if (base + 8 < end_off) {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ga + base + 8));
-                    d[2] = v.x; d[3] = v.y;
-                } else { d[2] = d[3] = 0; }
-                uint32_t be[12];   // be[k] = big-endian word of bytes base+k .. base+k+3
+                const unsigned long long base = filled + 4ull * lane;   // this lane converts positions base .. base+3
+                uint32_t d[3];                                          // stream bytes base .. base+11
 #pragma unroll
-                for (int k = 0; k < 12; k++)
-                    be[k] = __byte_perm(__funnelshift_r(d[k >> 2], d[(k >> 2) + 1 > 3 ? 3 : (k >> 2) + 1], 8 * (k & 3)), 0, 0x0123);
+                for (int k = 0; k < 3; k++)
+                    d[k] = (base + 4 * k < end_off) ? __ldg(reinterpret_cast<const uint32_t *>(ga + base + 4 * k)) : 0u;
+                uint32_t be[8];    // be[k] = big-endian word of bytes base+k .. base+k+3
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 8; k++)
+                    be[k] = __byte_perm(__funnelshift_r(d[k >> 2], d[(k >> 2) + 1 > 2 ? 2 : (k >> 2) + 1], 8 * (k & 3)), 0, 0x0123);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
                     const uint32_t idx = (uint32_t)((base + k) & (kWinPos - 1));
                     const uint2 e = make_uint2(be[k], be[k + 4]);
                     win[idx] = e;
@@ -568,7 +590,7 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             filled += kWinFill;
             __syncwarp();
         }
-        // ---- 512 symbols, state recurrence only; every lane computes the same values
+        // ---- kDecBlock symbols, state recurrence only
         uint32_t x = s.x;
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
         const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
@@ -583,10 +605,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
                     const uint32_t slot8 = x3 & ((kProbScale - 1) << SH);          // byte offset of the slot's entry
                     const uint32_t xs = x >> kProbBits;
                     uint2 e;
-                    if (SPLIT16) {
-                        e.x = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(f16) + slot8);
-                        e.y = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(b16) + slot8);
-                    } else e = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(ent) + slot8);
+                    e.x = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(f16) + slot8);
+                    e.y = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(b16) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
                     slots[g * 16 + b] = (uint16_t)slot8;
                     x = e.x * xs + e.y;
@@ -608,18 +628,12 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         s.x = x;
         s.pos += (unsigned long long)(wa - wa0) / 8;
         __syncwarp();
-        // ---- all lanes: slot -> symbol for 8 symbols each, one 8-byte store per lane
+        // ---- all lanes: slot -> symbol for 4 symbols each, one 4-byte store per lane
         {
-            const uint4 sv = *reinterpret_cast<const uint4 *>(slots + 8 * lane);
-            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
-            uint32_t ow[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> SH], b2 = symt[sw[2 * k] >> (16 + SH)];
-                const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> SH], d2 = symt[sw[2 * k + 1] >> (16 + SH)];
-                ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
-            }
-            *reinterpret_cast<uint2 *>(out + i + 8 * lane) = make_uint2(ow[0], ow[1]);
+            const uint2 sv = *reinterpret_cast<const uint2 *>(slots + 4 * lane);
+            const uint32_t a = symt[(sv.x & 0xffffu) >> SH], b2 = symt[sv.x >> (16 + SH)];
+            const uint32_t c2 = symt[(sv.y & 0xffffu) >> SH], d2 = symt[sv.y >> (16 + SH)];
+            *reinterpret_cast<uint32_t *>(out + i + 4 * lane) = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
         }
         __syncwarp();
         i += kDecBlock;
@@ -629,21 +643,15 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
                  cudaStream_t st) {
     if (n_streams <= 0) return;
-    const char *env = getenv("ALICE_RANS_DEC_SPLIT16");
-    const bool split16 = env ? env[0] == '1' : kDecSplit16Default;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        auto go = [&](auto k, int smem, unsigned long long &attr_done) {
+        const int smem = LPB * kDecSmemBytes;      // four-warp blocks: 105.6 KB, two per SM
 #ifndef ALICE_EMUL
-            ensure_dyn_smem(k, smem, attr_done);
-#else
-            (void)attr_done;
+        static unsigned long long attr_done = 0;
+        ensure_dyn_smem(k_rans_decode<LPB>, smem, attr_done);
 #endif
-            ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
-        };
-        static unsigned long long done_plain = 0, done_split = 0;
-        if (split16) go(k_rans_decode<LPB, true>, LPB * kDecSmemBytes16, done_split);
-        else go(k_rans_decode<LPB, false>, LPB * kDecSmemBytes, done_plain);
+        auto k = k_rans_decode<LPB>;
+        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
     });
 }
 

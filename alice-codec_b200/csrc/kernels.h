@@ -12,6 +12,18 @@ namespace alice {
 // coef_dump: optional i32 [3][pf*ph*pw] copy of the 3-D wavelet coefficients (parity tests), else null
 void forward_frontend(int wavelet, const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbols, unsigned *d_hist,
                       int w, int h, int f, int pw, int ph, int pf, int step, int32_t *d_coef_dump, cudaStream_t st);
+// The fused front-end (k_fwd_fused.cu): one launch for a batch of chunks of one shape, no plane scratch.  Eligible shapes:
+// 64 frames, even height, width a multiple of 16 (>= 80), 16-byte aligned RGB.  hist of the batch = [job][3][256], zeroed.
+struct FwdFusedJob {
+    const uint8_t *rgb;      // [64][h][w][3]
+    uint8_t *symbols;        // [3][64][h][w]
+    unsigned *hist;          // [3][256] of this chunk
+    int32_t *coef_dump;      // optional i32 [3][64][h][w] (parity tests; the launch must say dump = true), else null
+};
+bool forward_fused_eligible(const uint8_t *d_rgb, int w, int h, int f);
+void forward_frontend_fused(int wavelet, const FwdFusedJob *d_jobs, int n_jobs, bool dump, unsigned *d_hist_base, int w, int h,
+                            int step, int n_sms, cudaStream_t st);
+int device_sm_count();       // multiprocessors of the current device (cached)
 // symbols: u8 [3][pf*ph*pw]; coef: i32 [3][f][ph][pw] scratch; steps[3] = per-channel quant_step from the header
 void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f,
                      int pw, int ph, int pf, const int steps[3], cudaStream_t st);

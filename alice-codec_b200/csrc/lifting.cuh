@@ -88,6 +88,12 @@ template <int WT, bool WIDE> struct FwdLift {
         d2 = dd; e2 = s1;
         lo = s2; hi = dd;
     }
+    // The odd sample of a pushed pair only enters the state (the outputs of a push depend on the new EVEN sample and on
+    // older pairs), so a push can be split: push_even / push_even_steady with s[2j], then set_odd with s[2j+1].  A
+    // caller that produces the two samples one after the other (two image rows) never holds both.
+    ALICE_HD bool push_even(int en, int k, int j, int &lo, int &hi) { return push(en, o, k, j, lo, hi); }
+    ALICE_HD void push_even_steady(int en, int &lo, int &hi) { push_steady(en, o, lo, hi); }
+    ALICE_HD void set_odd(int on) { o = on; }
     // which = 0 .. NST-1; half = number of pairs in the whole line; k = pairs pushed so far (>= 1).
     ALICE_HD bool flush(int k, int which, int half, int &lo, int &hi) {
         if (NST == 1) {

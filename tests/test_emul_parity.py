@@ -28,7 +28,8 @@ def test_survey_kats(api, row):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 2, 2), (3, 5, 1), (5, 3, 3), (7, 2, 4), (2, 9, 5), (66, 6, 2),
-                                   (130, 4, 2), (6, 70, 2), (12, 6, 64), (256, 6, 2), (380, 10, 3), (260, 4, 64)])
+                                   (130, 4, 2), (6, 70, 2), (12, 6, 64), (256, 6, 2), (380, 10, 3), (260, 4, 64),
+                                   (80, 2, 64), (128, 6, 64), (112, 40, 64)])   # the last three: the fused front-end kernel
 @pytest.mark.parametrize("wavelet", [0, 1, 2])
 def test_odd_and_edge_shapes(api, shape, wavelet):
     w, h, f = shape
@@ -111,4 +112,4 @@ def test_errors_and_abi(api):
 
 
 def test_shared_workspace_batch(api):
-    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5)), n=3)
+    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5), (96, 4, 64)), n=3)

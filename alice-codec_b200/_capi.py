@@ -85,6 +85,7 @@ SIGNATURES = {
     "alice_codec_decode_stages": (vp, [vp, u64p, u8p]),
     "alice_codec_batch_create": (vp, [u8, u8, u32, u32, u32, u32, vp]),
     "alice_codec_batch_create_ex": (vp, [u8, u8, u32, u32, u32, u32, vp, u32]),
+    "alice_codec_batch_create_ex2": (vp, [u8, u8, u32, u32, u32, u32, vp, u32, u64]),
     "alice_codec_batch_workspace_bytes": (u64, [vp]),
     "alice_codec_batch_encode_device_ws": (cint, [vp, C.POINTER(vp), C.POINTER(vp), u32]),
     "alice_codec_batch_destroy": (None, [vp]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "alice_codec_synth_rgb_device": (cint, [cint, u32, u32, u32, u32, vp, vp]),
     "alice_codec_pinned_alloc": (vp, [u64]),
     "alice_codec_pinned_free": (None, [vp]),
+    "alice_codec_trim_host_pool": (None, []),
     "alice_codec_device_count": (cint, []),
     "alice_codec_set_device": (cint, [cint]),
 }

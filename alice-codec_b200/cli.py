@@ -34,8 +34,18 @@ def cmd_encode(a) -> None:
         per = a.width * a.height * 3
         if rgb.size != per * a.frames:
             raise pkg.CodecError(1, f"buffer size mismatch: expected {per * a.frames}, got {rgb.size}")
+        # the full-size chunks run as ONE batch (all their rANS streams concurrently); a shorter last chunk goes alone
+        n_full, rest = divmod(a.frames, a.chunk_frames)
         blobs = []
-        for t0 in range(0, a.frames, a.chunk_frames):
+        if n_full >= 2:
+            batch = pkg.ChunkBatch(a.quality, a.wavelet, a.width, a.height, a.chunk_frames, n_full)
+            cb = per * a.chunk_frames
+            parts = [np.ascontiguousarray(rgb[i * cb:(i + 1) * cb]) for i in range(n_full)]
+            blobs = [c.to_bytes() for c in batch.encode_host([p.ctypes.data for p in parts])]
+            batch.close()
+        else:
+            n_full = 0
+        for t0 in range(n_full * a.chunk_frames, a.frames, a.chunk_frames):
             nf = min(a.chunk_frames, a.frames - t0)
             blobs.append(enc.encode(rgb[t0 * per:(t0 + nf) * per], a.width, a.height, nf).to_bytes())
         data = sharding.concat_stream(blobs)
@@ -48,9 +58,23 @@ def cmd_encode(a) -> None:
                      f"({ratio * 100:.1f}% ratio, quality={a.quality}, wavelet={a.wavelet})\n")
 
 
+def _blobs(data: bytes):
+    """The .alc blobs of a file: a multi-chunk stream is split; anything after the last well-formed blob is ignored, as
+    EncodedChunk::from_bytes ignores trailing bytes (pipeline.rs:303).  A file that does not even hold one blob is
+    handed to from_bytes as is, which reports the reference's error."""
+    out, off = [], 0
+    while len(data) - off >= 3138 and data[off:off + 4] == b"ALCC":
+        n = 3138 + sum(int.from_bytes(data[off + 18 + 1040 * c:off + 22 + 1040 * c], "little") for c in range(3))
+        if off + n > len(data):
+            break
+        out.append(data[off:off + n])
+        off += n
+    return out or [data]
+
+
 def cmd_decode(a) -> None:
     data = open(a.input, "rb").read()
-    blobs = sharding.split_stream(data) if data[:4] == b"ALCC" and len(data) >= 3138 else [data]
+    blobs = _blobs(data)
     dec = pkg.FrameDecoder()
     with open(a.output, "wb") as f:
         total = 0
@@ -77,7 +101,7 @@ def cmd_info(a) -> None:
     print(f"  Payload:     {chunk.compressed_size} bytes")
     print(f"  Raw size:    {raw} bytes (uncompressed RGB)")
     print(f"  Ratio:       {ratio * 100:.1f}%")
-    n = len(sharding.split_stream(data)) if len(data) >= 3138 else 1
+    n = len(_blobs(data))
     if n > 1:
         print(f"  Chunks:      {n} (multi-chunk stream)")
 
@@ -101,6 +125,8 @@ def main(argv=None) -> int:
     i.add_argument("input")
     a = ap.parse_args(argv)
     try:
+        if a.command == "encode" and not 0 <= a.quality <= 255:            # the reference's -q is a u8 (main.rs:54)
+            raise ValueError(f"invalid value '{a.quality}' for '--quality': not in 0..=255")
         {"encode": cmd_encode, "decode": cmd_decode, "info": cmd_info}[a.command](a)
     except (ValueError, OSError) as ex:
         sys.stderr.write(f"error: {ex}\n")                 # main.rs:104-107

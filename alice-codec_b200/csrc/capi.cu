@@ -47,10 +47,13 @@ struct DevBuf {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// Rust's Box<[u8]> of length 0 is a dangling non-null pointer that data_free(ptr, 0) ignores (ffi.rs:288-296).  Empty
+// results get the address of this static byte: non-null, never malloc'ed, never freed.
+uint8_t g_empty_box;
 uint8_t *boxed_copy(const uint8_t *src, size_t len) {
-    // Rust's Box<[u8]> of length 0 is a dangling non-null pointer; we hand out a 1-byte block instead.
-    uint8_t *p = (uint8_t *)malloc(len ? len : 1);
-    if (p && len) memcpy(p, src, len);
+    if (len == 0) return &g_empty_box;
+    uint8_t *p = (uint8_t *)malloc(len);
+    if (p) memcpy(p, src, len);
     return p;
 }
 
@@ -197,10 +200,12 @@ Wavelet1D *alice_codec_wavelet1d_cdf97(void) { return new (std::nothrow) Wavelet
 void alice_codec_wavelet1d_destroy(Wavelet1D *p) { delete p; }
 
 void alice_codec_wavelet1d_forward(const Wavelet1D *wv, int32_t *data, uint32_t len) {
+    set_error(0, "");                     // void entry point: callers read alice_codec_last_error() afterwards
     if (!wv || !data || len < 2) return;  // ffi.rs:57
     wavelet_nd((uint8_t)wv->kind, false, data, len, 1, 1, 1);
 }
 void alice_codec_wavelet1d_inverse(const Wavelet1D *wv, int32_t *data, uint32_t len) {
+    set_error(0, "");
     if (!wv || !data || len < 2) return;  // ffi.rs:78
     wavelet_nd((uint8_t)wv->kind, true, data, len, 1, 1, 1);
 }
@@ -250,7 +255,7 @@ double alice_codec_psnr(const uint8_t *a, const uint8_t *b, uint32_t len) {
     return 10.0 * log10(255.0 * 255.0 / mse);
 }
 
-void alice_codec_data_free(uint8_t *ptr, uint32_t len) { if (ptr && len > 0) free(ptr); }
+void alice_codec_data_free(uint8_t *ptr, uint32_t len) { if (ptr && len > 0 && ptr != &g_empty_box) free(ptr); }
 void alice_codec_string_free(char *s) { free(s); }
 char *alice_codec_version(void) {
     const char v[] = "0.1.2";  // CARGO_PKG_VERSION of the reference this library is ABI-compatible with
@@ -295,7 +300,7 @@ EncodedChunk *alice_codec_chunk_from_bytes64(const uint8_t *data, uint64_t len) 
     if (Chunk::from_bytes(data, (size_t)len, c->c)) { delete c; return nullptr; }
     return c;
 }
-void alice_codec_data_free64(uint8_t *ptr, uint64_t) { free(ptr); }
+void alice_codec_data_free64(uint8_t *ptr, uint64_t) { if (ptr != &g_empty_box) free(ptr); }
 
 int alice_codec_rgb_to_ycocg_r(const uint8_t *rgb, uint64_t rgb_len, int16_t *y, int16_t *co, int16_t *cg,
                                uint64_t out_len) {
@@ -875,6 +880,11 @@ AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t 
 }
 AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32_t w, uint32_t h, uint32_t f,
                                         uint32_t n_chunks, void *cuda_stream, uint32_t flags) {
+    return alice_codec_batch_create_ex2(quality, wavelet, w, h, f, n_chunks, cuda_stream, flags, 0);
+}
+AliceBatch *alice_codec_batch_create_ex2(uint8_t quality, uint8_t wavelet, uint32_t w, uint32_t h, uint32_t f,
+                                         uint32_t n_chunks, void *cuda_stream, uint32_t flags,
+                                         uint64_t payload_bytes_per_chunk) {
     set_error(0, "");
     if (wavelet > 2 || n_chunks == 0) { set_error(kErrDimensions, "bad wavelet byte or n_chunks == 0"); return nullptr; }
     Dims d;
@@ -883,9 +893,12 @@ AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32
     if (!cuda_ready()) return nullptr;
     AliceBatch *b = new (std::nothrow) AliceBatch();
     if (!b) return nullptr;
-    // single chunks keep the worst-case payload capacity; batches budget N/3 + 64 KiB per stream and fall
-    // back to a worst-case buffer for any stream that overflows (Engine::run_rans_encode)
-    const uint64_t cap = n_chunks == 1 ? 0 : d.padded / 3 + 65536;
+    // Payload arena.  Single chunks keep the worst case (two bytes per symbol); batches budget N + 192 KiB per chunk, or
+    // what the caller says its chunks need on average (the streams are placed back to back, so the arena only has to
+    // hold the batch's real payload); a stream that finds no room falls back to a worst-case buffer of its own
+    // (Engine::run_rans_encode).
+    uint64_t cap = n_chunks == 1 ? 0 : d.padded / 3 + 65536;
+    if (payload_bytes_per_chunk) cap = payload_bytes_per_chunk / 3 + 16;
     b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false,
                                        (flags & ALICE_BATCH_SHARED_WORKSPACE) != 0);
     if (!b->eng || !b->eng->ok()) { delete b->eng; delete b; return nullptr; }
@@ -946,12 +959,16 @@ int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, ui
     int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr,
                               shared ? b->work_ptrs.data() : nullptr);
     if (rc) return rc;
+    std::vector<Chunk *> cks(n);
     for (uint32_t i = 0; i < n; i++) {
-        out_chunks[i] = alice_codec_batch_get_chunk(b, i);
-        if (!out_chunks[i]) {
-            for (uint32_t k = 0; k < i; k++) { delete out_chunks[k]; out_chunks[k] = nullptr; }
-            return last_error_code() ? last_error_code() : kErrCuda;
-        }
+        out_chunks[i] = new (std::nothrow) EncodedChunk();
+        if (!out_chunks[i]) { rc = kErrCuda; set_error(kErrCuda, "host allocation failed"); }
+        else cks[i] = &out_chunks[i]->c;
+    }
+    if (!rc) rc = e->fetch_chunks(n, cks.data());     // every payload copy enqueued, one synchronisation
+    if (rc) {
+        for (uint32_t k = 0; k < n; k++) { delete out_chunks[k]; out_chunks[k] = nullptr; }
+        return rc;
     }
     return kOk;
 }
@@ -1022,6 +1039,7 @@ void *alice_codec_pinned_alloc(uint64_t bytes) {
     return p;
 }
 void alice_codec_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+void alice_codec_trim_host_pool(void) { trim_pinned_pool(); }
 int alice_codec_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -48,7 +48,7 @@ size_t g_buf_pool_bytes = 0;
 size_t buf_pool_limit() {
     static size_t lim = [] {
         const char *e = getenv("ALICE_CODEC_PINNED_POOL_MB");
-        long long mb = e ? atoll(e) : 16384;
+        long long mb = e ? atoll(e) : 1024;   // idle page-locked memory kept for reuse; raise it for sustained batch traffic
         return (size_t)(mb < 0 ? 0 : mb) << 20;
     }();
     return lim;
@@ -71,7 +71,8 @@ bool ByteBuf::acquire_pinned(size_t n) {
         std::lock_guard<std::mutex> lk(g_buf_mu);
         size_t best = g_buf_pool.size();
         for (size_t i = 0; i < g_buf_pool.size(); i++)
-            if (g_buf_pool[i].cap >= n && (best == g_buf_pool.size() || g_buf_pool[i].cap < g_buf_pool[best].cap)) best = i;
+            if (g_buf_pool[i].cap >= n && g_buf_pool[i].cap <= 2 * n + 65536 &&   // never hand a small chunk a huge buffer
+                (best == g_buf_pool.size() || g_buf_pool[i].cap < g_buf_pool[best].cap)) best = i;
         if (best != g_buf_pool.size()) {
             p_ = g_buf_pool[best].p;
             cap_ = g_buf_pool[best].cap;
@@ -116,6 +117,20 @@ void ByteBuf::release() {
     p_ = nullptr;
     n_ = cap_ = 0;
     pinned_ = false;
+}
+
+void trim_pinned_pool() {
+    std::vector<PoolEntry2> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_buf_mu);
+        drop.swap(g_buf_pool);
+        g_buf_pool_bytes = 0;
+    }
+    for (PoolEntry2 &e : drop) {
+        cudaHostUnregister(e.p);
+        cudaGetLastError();
+        free(e.p);
+    }
 }
 
 // ------------------------------------------------------------------------- .alc container
@@ -286,12 +301,24 @@ uint8_t *Engine::rgb_stage(uint32_t slot) {
 int Engine::run_rans_encode(uint32_t n) {
     const size_t N = (size_t)d_.padded;
     const uint32_t S = n * 3;
+    // Payload placement: the streams go back to back into the engine's payload arena (cap_ * 3 * pay_cap_ bytes), each with
+    // the upper bound that its histogram and table give (k_estimate_stream_bytes) instead of a fixed slot, so the arena
+    // only has to hold what the batch really produces (+ 0.03 %).  A stream that does not fit any more gets no room at all
+    // and goes through the overflow path below.
+    estimate_stream_bytes(d_hist_, d_enc_, (int)S, N, d_results_, st_);
+    CU_TRY(cudaMemcpyAsync(h_results_, d_results_, S * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
+    CU_TRY(cudaStreamSynchronize(st_));
+    const size_t arena = (size_t)cap_ * 3 * pay_cap_;
+    size_t used = 0;
     for (uint32_t s = 0; s < S; s++) {
+        const size_t want = (size_t)h_results_[s];
+        const bool fits = used + want <= arena;
         h_enc_jobs_[s].symbols = sym_ptr_[s / 3] + (size_t)(s % 3) * N;
         h_enc_jobs_[s].n = N;
-        h_enc_jobs_[s].out = d_payload_ + (size_t)s * pay_cap_;
-        h_enc_jobs_[s].cap = pay_cap_;
+        h_enc_jobs_[s].out = d_payload_ + used;
+        h_enc_jobs_[s].cap = fits ? want : 0;
         stream_base_[s] = h_enc_jobs_[s].out;
+        if (fits) used += want;
     }
     CU_TRY(cudaMemcpyAsync(d_enc_jobs_, h_enc_jobs_, S * sizeof(RansEncJob), cudaMemcpyHostToDevice, st_));
     rans_encode(d_enc_jobs_, d_enc_, d_hist_, d_results_, (int)S, st_);
@@ -356,6 +383,7 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     // the two-kernel path, which finishes reading the RGB before the first symbol is written.
     auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
     bool all_fused = true;
+    if (const char *e = getenv("ALICE_FWD_FUSED")) all_fused = e[0] != '0';   // measurement hook (tools/frontend_time.py), removed once decided
     for (uint32_t c = 0; c < n; c++)
         all_fused = all_fused && forward_fused_eligible(d_rgb[c], (int)d_.w, (int)d_.h, (int)d_.f) &&
                     (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0;
@@ -391,7 +419,8 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     return kOk;
 }
 
-int Engine::fetch_chunk(uint32_t i, Chunk &out) {
+// headers of chunk i + the device->host copies of its payload, enqueued on the engine's stream (no synchronisation)
+int Engine::fetch_enqueue(uint32_t i, Chunk &out, bool &direct) {
     if (i >= last_n) { set_error(kErrBufferSize, "chunk index out of range"); return kErrBufferSize; }
     out.width = d_.w; out.height = d_.h; out.frames = d_.f;
     out.wavelet = last_wavelet;
@@ -408,7 +437,7 @@ int Engine::fetch_chunk(uint32_t i, Chunk &out) {
     }
     // payload: the device writes straight into the chunk's page-locked buffer (pooled, see ByteBuf)
     uint8_t *dst = nullptr;
-    const bool direct = out.data.acquire_pinned(total);
+    direct = out.data.acquire_pinned(total);
     if (direct) dst = out.data.data();
     else {
         if (!ensure_pinned_payload(total)) return kErrCuda;
@@ -422,8 +451,37 @@ int Engine::fetch_chunk(uint32_t i, Chunk &out) {
                                    cudaMemcpyDeviceToHost, st_));
         off += stream_len_[s];
     }
+    return kOk;
+}
+
+int Engine::fetch_chunk(uint32_t i, Chunk &out) {
+    bool direct = false;
+    int rc = fetch_enqueue(i, out, direct);
+    if (rc) return rc;
     CU_TRY(cudaStreamSynchronize(st_));
-    if (!direct && !out.data.assign(h_pay_, total)) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
+    if (!direct) {
+        size_t total = 0;
+        for (int c = 0; c < 3; c++) total += out.ch[c].compressed_len;
+        if (!out.data.assign(h_pay_, total)) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
+    }
+    return kOk;
+}
+
+// All n chunks of the last encode: every payload copy is enqueued first, ONE synchronisation at the end (a chunk whose
+// page-locked buffer cannot be had goes through the single staging buffer and synchronises on its own).
+int Engine::fetch_chunks(uint32_t n, Chunk *const *out) {
+    for (uint32_t i = 0; i < n; i++) {
+        bool direct = false;
+        int rc = fetch_enqueue(i, *out[i], direct);
+        if (rc) return rc;
+        if (!direct) {
+            CU_TRY(cudaStreamSynchronize(st_));
+            size_t total = 0;
+            for (int c = 0; c < 3; c++) total += out[i]->ch[c].compressed_len;
+            if (!out[i]->data.assign(h_pay_, total)) { set_error(kErrCuda, "host allocation failed"); return kErrCuda; }
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(st_));
     return kOk;
 }
 
@@ -458,6 +516,11 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
 
 int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out) {
     if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    // This call reuses the histogram, table, payload and overflow buffers of the last encode: whatever encode_device left
+    // resident is gone afterwards (fetch_chunk / decode_device_resident then report "out of range" instead of returning
+    // another batch's data).
+    last_n = 0;
+    for (size_t s = 0; s < stream_base_.size(); s++) { stream_base_[s] = nullptr; stream_len_[s] = 0; stream_off_[s] = 0; }
     if (shared_ws_)   // the symbol planes of chunk i live in its output buffer (>= workspace_bytes()) until the last kernel
         for (uint32_t i = 0; i < n; i++) sym_ptr_[i] = d_rgb_out[i];
     const size_t N = (size_t)d_.padded;
@@ -482,6 +545,8 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             off += ck.ch[c].compressed_len;
         }
     }
+    const size_t arena = (size_t)cap_ * 3 * pay_cap_;
+    size_t arena_used = 0;
     for (uint32_t i = 0; i < n; i++) {
         const Chunk &ck = *chunks[i];
         size_t off = 0;
@@ -494,8 +559,8 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             const uint32_t s = i * 3 + c;
             memcpy(h_hist_ + (size_t)s * 256, ck.ch[c].histogram, 256 * sizeof(uint32_t));
             const size_t len = ck.ch[c].compressed_len;
-            uint8_t *dst = d_payload_ + (size_t)s * pay_cap_;
-            if (len > pay_cap_) {
+            uint8_t *dst = d_payload_ + arena_used;
+            if (arena_used + round_up(len, 16) + 16 > arena) {
                 const size_t full = std::max(round_up(len, 16), rans_enc_worst_case(N));
                 if (overflow_bufs_[s]) { cudaFree(overflow_bufs_[s]); overflow_bufs_[s] = nullptr; }
                 if (!dev_alloc(overflow_bufs_[s], full, dev_bytes_)) {
@@ -503,7 +568,7 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
                     return kErrCuda;
                 }
                 dst = overflow_bufs_[s];
-            }
+            } else arena_used += round_up(len, 16) + 16;   // (the decoder's window refill reads whole words past the end)
             if (len) {
                 // host vector -> pinned staging -> device; the staging buffer is reused once the copy has landed
                 const uint8_t *src = ck.data.data() + off;

@@ -101,6 +101,8 @@ public:
                       int32_t *d_coef_dump, uint8_t *const *d_work = nullptr);
     // Fill a Chunk (headers + payload copied to the host) from the last encode_device.
     int fetch_chunk(uint32_t i, Chunk &out);
+    // The first n chunks of the last encode_device at once: all payload copies enqueued, one synchronisation.
+    int fetch_chunks(uint32_t n, Chunk *const *out);
     // Decode the payloads the last encode_device left on the device.
     int decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n);
     // Upload n host chunks (headers + payload) and decode them into device buffers d_rgb_out[i].
@@ -117,6 +119,7 @@ public:
 
 private:
     int run_rans_encode(uint32_t n);
+    int fetch_enqueue(uint32_t i, Chunk &out, bool &direct);
     Dims d_;
     uint32_t cap_ = 0;
     uint64_t pay_cap_ = 0;
@@ -157,5 +160,6 @@ private:
 Engine *acquire_engine(const Dims &d);
 void release_engine(Engine *e);
 bool cuda_ready();   // a device is present and usable; sets the CUDA error otherwise
+void trim_pinned_pool();   // release the idle page-locked payload buffers (ByteBuf pool)
 
 }  // namespace alice

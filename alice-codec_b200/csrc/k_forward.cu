@@ -409,7 +409,7 @@ static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbo
 #ifndef ALICE_XY_WPB
 #define ALICE_XY_WPB 1             // one warp per block: 1.37 -> 1.19 ms per 1080p x 64 chunk vs four (measured)
 #endif
-    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * ALICE_XY_TARGET_WARPS + base_warps - 1) / base_warps),
+    int n_segs = (int)std::min<long long>(std::max<long long>(1, (device_sm_count() * ALICE_XY_TARGET_WARPS + base_warps - 1) / base_warps),
                                           std::max(1, halfy / 16));
     int seg_pairs = (halfy + n_segs - 1) / n_segs;
     n_segs = (halfy + seg_pairs - 1) / seg_pairs;
@@ -425,7 +425,7 @@ static void launch_fwd(const uint8_t *d_rgb, int16_t *d_planes, uint8_t *d_symbo
     const size_t frame_sz = (size_t)pw * ph;
     const int vec = (pw % 4 == 0) ? 4 : 2;
     const long long items = frame_sz / vec;
-    const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+    const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 8);
     const dim3 tgrid(gx, 1, 3), block(256);
     if (vec == 4 && pf == 64) {
         auto kt = k_fwd_t_quant<WT, 4, 64>;

@@ -93,11 +93,14 @@ k_fwd_fused(const FwdFusedJob *__restrict__ jobs, int w, int h, int n_strips, in
     }
     __syncthreads();
 
-    // warp 0: fetch the rows of pairs [jg, jg + nq) of all NFR frames into ring stages 0 .. nq-1
+    // Fetch the rows of pairs [jg, jg + nq) of all NFR frames into ring stages 0 .. nq-1: at most one 208-byte bulk copy
+    // per thread.  (A bulk copy takes its operands from uniform registers, so a warp issues the copies of its lanes one
+    // after the other, ~8 instructions each: spread over all warps they cost every warp a few hundred issue slots per
+    // group; issued by one warp they made the whole block wait for it at the next barrier.)
     auto issue_group = [&](int jg, int nq) {
-        if (lane == 0)
+        if (tid == 0)
             for (int i = 0; i < nq; i++) mbar_arrive_expect_tx(&bar[i], (unsigned)(NFR * 2 * kFsRowBytes));
-        for (int idx = lane; idx < nq * NFR * 2; idx += 32) {
+        for (int idx = tid; idx < nq * NFR * 2; idx += NT) {
             const int st = idx / (NFR * 2), r = idx - st * (NFR * 2);
             const int y = 2 * (jg + st) + (r & 1);
             const uint8_t *src = job.rgb + ((size_t)(fr0 + (r >> 1)) * h + y) * rowbytes + a;
@@ -115,22 +118,21 @@ k_fwd_fused(const FwdFusedJob *__restrict__ jobs, int w, int h, int n_strips, in
             const int xh = col / kFsVP, pair = kFsVP * s + (col - xh * kFsVP);
             if (pair >= halfx) continue;
             const int jo = jo_first + qq;
-            const size_t pos = (size_t)(row ? halfy + jo : jo) * w + (xh ? halfx + pair : pair);
+            const uint32_t pos = (uint32_t)(row ? halfy + jo : jo) * (uint32_t)w + (uint32_t)(xh ? halfx + pair : pair);
             const int16_t *src = tbuf + qq * (NFR * kFsFrameI16) + r;
-            const size_t plane = (size_t)ch * 64 * fs;
-            uint8_t *pl = job.symbols + plane + (size_t)(16 * twin) * fs + pos;   // low-t symbol of the next pair to come out
-            uint8_t *ph = pl + 32 * fs;                                           // its high-t symbol
-            int32_t *cl = DUMP ? job.coef_dump + plane + (size_t)(16 * twin) * fs + pos : nullptr;
+            // symbol offsets fit 32 bits (3 * 64 * w * h < 2^32 is checked by the launcher)
+            const uint32_t fs32 = (uint32_t)fs;
+            uint32_t ol = ((uint32_t)ch * 64u + 16u * (uint32_t)twin) * fs32 + pos;   // low-t symbol of the next pair to come out
+            const uint32_t hi_delta = 32u * fs32;                                     // its high-t symbol
             unsigned *hist = sh_hist + ch * 256;
             auto emit = [&](int lo, int hi) {
                 const uint32_t sl = quant_symbol(lo, q), sh = quant_symbol(hi, q);
-                *pl = (uint8_t)sl;
-                *ph = (uint8_t)sh;
+                job.symbols[ol] = (uint8_t)sl;
+                job.symbols[ol + hi_delta] = (uint8_t)sh;
                 if (sl) atomicAdd(&hist[sl], 1u);      // bin 0 is filled in afterwards: N - sum of the others
                 if (sh) atomicAdd(&hist[sh], 1u);
-                if (DUMP) { cl[0] = lo; cl[32 * fs] = hi; cl += fs; }
-                pl += fs;
-                ph += fs;
+                if (DUMP) { job.coef_dump[ol] = lo; job.coef_dump[ol + hi_delta] = hi; }
+                ol += fs32;
             };
             FwdLift<WT, false> T;
             int lo, hi;
@@ -223,7 +225,7 @@ k_fwd_fused(const FwdFusedJob *__restrict__ jobs, int w, int h, int n_strips, in
     int n_acc = 0;        // finished row pairs waiting in the t buffer
     int jo_first = 0;     // row pair index of t-buffer slot 0
     const int n_groups = (je - js + Q - 1) / Q;
-    if (wv == 0 && n_groups > 0) issue_group(js, min(Q, je - js));
+    if (n_groups > 0) issue_group(js, min(Q, je - js));
     // One group of row pairs.  FIRST = the tile's first group: its first NST + 1 steps are the warm-up / top-edge steps of
     // the lifting state machines (general push); every later group runs the branch-free steady form only.  Two copies of
     // the body, so that the 60 registers of lifting state never flow through a join of the two forms.
@@ -278,7 +280,7 @@ k_fwd_fused(const FwdFusedJob *__restrict__ jobs, int w, int h, int n_strips, in
             }
         }
         __syncthreads();   // every read of the ring is done, the t buffer is complete
-        if (wv == 0 && g + 1 < n_groups) issue_group(jg + Q, min(Q, je - (jg + Q)));
+        if (g + 1 < n_groups) issue_group(jg + Q, min(Q, je - (jg + Q)));
         if (n_acc) t_phase(n_acc, jo_first);
         __syncthreads();   // the t buffer is free again
         n_acc = 0;
@@ -320,6 +322,7 @@ __global__ void k_hist_zero_bin_batch(unsigned *__restrict__ hist, unsigned n_sy
 }
 
 bool forward_fused_eligible(const uint8_t *d_rgb, int w, int h, int f) {
+    if ((unsigned long long)w * (unsigned long long)h * 192ull >= (1ull << 32)) return false;   // 32-bit symbol offsets
     return f == 64 && (h & 1) == 0 && h >= 2 && (w & 15) == 0 && w >= 80 && (reinterpret_cast<uintptr_t>(d_rgb) & 15) == 0;
 }
 

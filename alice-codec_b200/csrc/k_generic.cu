@@ -68,7 +68,7 @@ __global__ void k_reorder(const int32_t *__restrict__ in, int32_t *__restrict__ 
 
 static unsigned grid_for(long long total, int block) {
     long long b = (total + block - 1) / block;
-    return (unsigned)std::max<long long>(1, std::min<long long>(b, (long long)kNumSMs * 16));
+    return (unsigned)std::max<long long>(1, std::min<long long>(b, (long long)device_sm_count() * 16));
 }
 
 void lift_axis(int32_t *d_data, int32_t *d_tmp, int wavelet, bool inverse, int axis, long long w, long long h,

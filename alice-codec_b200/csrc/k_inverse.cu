@@ -360,7 +360,7 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
     {
         const int vec = (pw % 4 == 0) ? 4 : 2;
         const long long items = frame_sz / vec;
-        const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, kNumSMs * 8);
+        const unsigned gx = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 8);
         const dim3 tgrid(gx, 1, 3), tblock(256);
         // (a FULLY unrolled PF = 64 instantiation spilled 1.4-1.9 KB per thread and measured 2.3x slower than the
         //  runtime loop; the rolled compile-time-depth form is 4 % faster than the runtime loop on the whole back-end)
@@ -385,7 +385,7 @@ static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb
 #ifndef ALICE_YX_WPB
 #define ALICE_YX_WPB 1
 #endif
-    int n_segs = (int)std::min<long long>(std::max<long long>(1, (kNumSMs * ALICE_YX_TARGET_WARPS + base_warps - 1) / base_warps),
+    int n_segs = (int)std::min<long long>(std::max<long long>(1, (device_sm_count() * ALICE_YX_TARGET_WARPS + base_warps - 1) / base_warps),
                                           std::max(1, halfy / 16));
     int seg_pairs = (halfy + n_segs - 1) / n_segs;
     n_segs = (halfy + seg_pairs - 1) / seg_pairs;

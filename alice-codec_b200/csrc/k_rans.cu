@@ -31,6 +31,7 @@
 // bytes come from a shared "window" table holding, for every byte position, the next eight
 // bytes as two big-endian words (8 bytes per position: the renormalisation shift in bits is
 // the address increment), so renormalisation is two selects and one funnel shift.
+#include <math.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -157,6 +158,47 @@ void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *
     if (n_streams <= 0) return;
     ALICE_LAUNCH(k_build_tables, dim3(n_streams), dim3(256), 0, st, d_hist, n_symbols, d_enc, d_dec_lut, d_aux,
                  d_freq, d_cum, d_lut8);
+}
+
+// ------------------------------------------------------------------- stream size estimate
+// Upper bound on the bytes a stream will take, from its histogram and table alone, so that a batch can place its
+// payloads back to back instead of reserving a fixed slot per stream.  A step multiplies the state by at most
+// (4096 / freq) * (1 + 2^-10) -- x' = 4096 * floor(x / f) + (x mod f) + cum < 4096 * (x / f + 2) with x / f >= 2^11 -- so the
+// stream holds at most sum(hist * log2(4096 / freq)) / 8 + n * log2(1 + 2^-10) / 8 bytes + the 4 state bytes; the
+// estimate adds n / 4096 + the encoder's block slack.  Streams that use the out-of-range last symbol of a malformed
+// table (freq > 4096 or 0: SURVEY.md 0.7) get the worst case of two bytes per symbol.
+__global__ void ALICE_LAUNCH_BOUNDS(256, 1)
+k_estimate_stream_bytes(const unsigned *__restrict__ hist, const EncSym *__restrict__ enc, unsigned long long n_symbols,
+                        unsigned long long *__restrict__ est) {
+    __shared__ double s_bits[8];
+    __shared__ int s_bad;
+    const int stream = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    const unsigned h = hist[(size_t)stream * 256 + tid];
+    const EncSym e = enc[(size_t)stream * 256 + tid];
+    double bits = 0.0;
+    if (h) {
+        if (e.packed & (kEncWide | kEncZero)) s_bad = 1;
+        else bits = (double)h * log2(4096.0 / (double)(kProbScale - e.cmpl));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(kFullMask, bits, d);
+    if ((tid & 31) == 0) s_bits[tid >> 5] = bits;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; i++) t += s_bits[i];
+        unsigned long long b = (unsigned long long)(t / 8.0) + n_symbols / 4096 + 4 + kRansEncSlack + 64;
+        const unsigned long long worst = rans_enc_worst_case(n_symbols);
+        est[stream] = (s_bad || b > worst) ? worst : (b + 15) / 16 * 16;
+    }
+}
+
+void estimate_stream_bytes(const unsigned *d_hist, const EncSym *d_enc, int n_streams, unsigned long long n_symbols,
+                           unsigned long long *d_est, cudaStream_t st) {
+    if (n_streams <= 0) return;
+    ALICE_LAUNCH(k_estimate_stream_bytes, dim3(n_streams), dim3(256), 0, st, d_hist, d_enc, n_symbols, d_est);
 }
 
 // --------------------------------------------------------------------------------- encode

@@ -313,7 +313,7 @@ cudaError_t rdo_seq_sums(const RdoViewHost *h_views, int n_views, double *h_acc,
     auto fail = [&](cudaError_t err) { return err; };
     if ((e = cudaMemcpyAsync(d_views, hv, sizeof(RdoView) * n_views, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e);
     if ((e = cudaMemsetAsync(d_state, 0, sizeof(RdoState) * 8, st)) != cudaSuccess) return fail(e);
-    const int gx = (int)std::min<unsigned long long>((max_n + 255) / 256, (unsigned long long)kNumSMs * 8);
+    const int gx = (int)std::min<unsigned long long>((max_n + 255) / 256, (unsigned long long)device_sm_count() * 8);
     if (max_n) {
         ALICE_LAUNCH(k_rdo_sum, dim3(gx ? gx : 1, n_views), dim3(256), 0, st, d_views, d_state);
     }
@@ -343,7 +343,7 @@ void rdo_quantize_volume(const int32_t *d_in, int32_t *d_out, unsigned w, unsign
     if (!n) return;
     RdoQuant q;
     for (int i = 0; i < 8; i++) { q.dz[i] = dz[i]; q.recip[i] = recip[i]; q.shift[i] = shift[i]; }
-    const int gx = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)kNumSMs * 16);
+    const int gx = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)device_sm_count() * 16);
     ALICE_LAUNCH(k_rdo_quantize, dim3(gx), dim3(256), 0, st, d_in, d_out, w, h, d, q);
 }
 

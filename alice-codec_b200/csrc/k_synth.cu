@@ -43,7 +43,7 @@ __global__ void k_synth(int kind, uint32_t seed, int w, int h, int f, uint8_t *_
 void synth_rgb(int kind, uint32_t seed, int w, int h, int f, uint8_t *d_rgb, cudaStream_t st) {
     const unsigned long long n = (unsigned long long)w * h * f;
     if (!n) return;
-    unsigned gx = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)kNumSMs * 32);
+    unsigned gx = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)device_sm_count() * 32);
     ALICE_LAUNCH(k_synth, dim3(gx), dim3(256), 0, st, kind, seed, w, h, f, d_rgb);
 }
 

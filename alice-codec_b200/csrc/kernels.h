@@ -44,7 +44,7 @@ struct DecAux {          // per stream
 // the encoder checks for output room once per 512-symbol block, so a stream buffer must hold the worst case
 // (2 bytes per symbol + 4 state bytes, rans.rs:269-308) plus one block of slack
 constexpr size_t kRansEncSlack = 1104;
-inline size_t rans_enc_worst_case(size_t n_symbols) { return (2 * n_symbols + 4 + kRansEncSlack + 15) / 16 * 16; }
+ALICE_HD size_t rans_enc_worst_case(size_t n_symbols) { return (2 * n_symbols + 4 + kRansEncSlack + 15) / 16 * 16; }
 constexpr int kEncTableBytes = 256 * (int)sizeof(EncSym);
 constexpr int kDecLutEntries = 4096;
 
@@ -52,6 +52,10 @@ constexpr int kDecLutEntries = 4096;
 // freq/cum u16 [n_streams][256] (optional, may be null).  n_symbols <= 256 (256 in the pipeline).
 void build_tables(const unsigned *d_hist, int n_streams, int n_symbols, EncSym *d_enc, uint32_t *d_dec_lut,
                   DecAux *d_aux, uint16_t *d_freq, uint16_t *d_cum, uint8_t *d_lut8, cudaStream_t st);
+
+// est[i] = upper bound on the bytes stream i will take (multiple of 16, includes the encoder's slack), from hist + enc
+void estimate_stream_bytes(const unsigned *d_hist, const EncSym *d_enc, int n_streams, unsigned long long n_symbols,
+                           unsigned long long *d_est, cudaStream_t st);
 
 struct RansEncJob {      // device-visible description of one stream to encode
     const uint8_t *symbols;

@@ -177,12 +177,22 @@ AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t 
                                      uint32_t frames, uint32_t n_chunks, void *cuda_stream);
 /* flags: ALICE_BATCH_SHARED_WORKSPACE — the batch owns no symbol planes (3 bytes per padded pixel and chunk): with
  * device pointers the caller passes one workspace of alice_codec_batch_workspace_bytes() per chunk to
- * alice_codec_batch_encode_device_ws (it may be the chunk's RGB input itself, or the buffer the chunk is decoded
- * into later: decode finishes reading the planes before it writes RGB); with host pointers the batch's RGB staging
- * buffers double as the workspace.  Saves 3 B/px of device memory per chunk in flight. */
+ * alice_codec_batch_encode_device_ws.  Chunks are encoded in index order, so workspace i may be the RGB buffer of any
+ * chunk j < i (already consumed), or the buffer chunk i is decoded into later (decode finishes reading the planes
+ * before it writes RGB).  It may even be chunk i's own RGB input, but that chunk then takes the slower two-kernel
+ * front-end (the fused kernel reads RGB and writes symbols in the same launch).  With host pointers the batch's RGB
+ * staging buffers double as the workspaces (chunk i's planes live in the staging buffer of chunk i-1).
+ * Saves 3 B/px of device memory per chunk in flight. */
 enum { ALICE_BATCH_SHARED_WORKSPACE = 1 };
 AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32_t width, uint32_t height,
                                         uint32_t frames, uint32_t n_chunks, void *cuda_stream, uint32_t flags);
+/* payload_bytes_per_chunk: device memory reserved for the encoded payload, per chunk on average (0 = the default, one
+ * byte per padded pixel + 192 KiB).  The batch places its streams back to back, each with the upper bound its histogram
+ * gives, so this only has to cover what the chunks really compress to; a stream that finds no room is redone in a
+ * worst-case buffer of its own (slow, never wrong). */
+AliceBatch *alice_codec_batch_create_ex2(uint8_t quality, uint8_t wavelet, uint32_t width, uint32_t height,
+                                         uint32_t frames, uint32_t n_chunks, void *cuda_stream, uint32_t flags,
+                                         uint64_t payload_bytes_per_chunk);
 uint64_t alice_codec_batch_workspace_bytes(const AliceBatch *b);
 int alice_codec_batch_encode_device_ws(AliceBatch *b, const uint8_t *const *d_rgb, uint8_t *const *d_workspace,
                                        uint32_t n);
@@ -192,7 +202,11 @@ void alice_codec_batch_destroy(AliceBatch *b);
 int alice_codec_batch_encode_device(AliceBatch *b, const uint8_t *const *d_rgb, uint32_t n);
 /* decodes what the last encode left on the device into d_rgb_out[i] (tables rebuilt from the histograms) */
 int alice_codec_batch_decode_device(AliceBatch *b, uint8_t *const *d_rgb_out, uint32_t n);
-/* host-buffer variants: host<->device copies are part of the call */
+/* host-buffer variants: host<->device copies are part of the call.  encode_host returns after ONE stream
+ * synchronisation for the whole batch (every payload copy is enqueued first).
+ * Call order: alice_codec_batch_decode_host reuses the histogram / table / payload buffers of the batch, so whatever
+ * the last encode left resident on the device is gone afterwards: alice_codec_batch_get_chunk and
+ * alice_codec_batch_decode_device then fail with ALICE_ERR_BUFFER_SIZE until the next encode. */
 int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, uint32_t n, EncodedChunk **out_chunks);
 int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chunks, uint32_t n,
                                   uint8_t *const *h_rgb_out);
@@ -213,6 +227,9 @@ int alice_codec_psnr_device(const uint8_t *d_a, const uint8_t *d_b, uint64_t len
 /* pinned host memory helpers for the host-buffer batch API */
 void *alice_codec_pinned_alloc(uint64_t bytes);
 void alice_codec_pinned_free(void *p);
+/* Encoded payloads live in page-locked host buffers that the library pools for reuse (idle pool bounded by the
+ * environment variable ALICE_CODEC_PINNED_POOL_MB, default 1024); this releases the idle ones. */
+void alice_codec_trim_host_pool(void);
 /* number of CUDA devices visible (0 if none / no driver); select the device for this thread */
 int alice_codec_device_count(void);
 int alice_codec_set_device(int device);

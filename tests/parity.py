@@ -446,3 +446,35 @@ def check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5)), n=3):
             except pkg.CodecError as e:
                 assert e.kind == "NullArgument"
             batch.close()
+
+
+def check_payload_arena(api, w=48, h=20, f=8, n=4):
+    """The batch places its rANS streams back to back in one payload arena, each with the upper bound its histogram gives
+    (k_estimate_stream_bytes): with a budget just above the real payload everything fits, with a budget far below it the
+    streams that find no room go through the worst-case retry -- the output is the oracle's either way."""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"        # the emulator treats host memory as device memory
+    rgbs = [O.generate(O.G2 if i == 1 else O.G1, w, h, f, O.SEED + i) for i in range(n)]
+    for q, wv in ((80, 1), (100, 0)):
+        refs = [O.encode(r, w, h, f, q, wv) for r in rgbs]
+        outs = [O.decode(r) for r in refs]
+        avg = sum(len(r) - 3138 for r in refs) // n
+        for budget in (avg + 4096, avg // 2, 64):
+            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=0, api=api, payload_bytes_per_chunk=budget)
+            d_in = [torch.from_numpy(r.copy()).to(dev) for r in rgbs]
+            d_out = [torch.zeros_like(t) for t in d_in]
+            batch.encode_device([t.data_ptr() for t in d_in])
+            for i in range(n):
+                assert batch.get_chunk(i).to_bytes() == refs[i], (q, wv, budget, i)
+            batch.decode_device([t.data_ptr() for t in d_out])
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            for i in range(n):
+                assert np.array_equal(d_out[i].cpu().numpy(), outs[i]), (q, wv, budget, i)
+            # foreign payloads through the same arena (decode_host places them back to back as well)
+            chunks = [pkg.EncodedChunk.from_bytes(r, api=api) for r in refs]
+            h_out = [torch.zeros(r.size, dtype=torch.uint8) for r in rgbs]
+            batch.decode_host(chunks, [t.data_ptr() for t in h_out])
+            for i in range(n):
+                assert np.array_equal(h_out[i].numpy(), outs[i]), (q, wv, budget, i)
+            batch.close()

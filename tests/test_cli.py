@@ -43,6 +43,13 @@ def test_info_and_errors_need_no_device(tmp_path):
     (tmp_path / "a.rgb").write_bytes(rgb.tobytes())
     r = run("encode", str(tmp_path / "a.rgb"), "-W", "8", "-H", "8", "-f", "2", "-w", "dct", "-o", str(tmp_path / "x.alc"))
     assert r.returncode == 1 and "unknown wavelet 'dct'; expected cdf53, cdf97, or haar" in r.stderr
+    # a single blob with trailing junk is still one chunk (from_bytes ignores trailing bytes, pipeline.rs:303)
+    (tmp_path / "junk.alc").write_bytes(alc + b"trailing bytes that are not a blob" * 100)
+    r = run("info", str(tmp_path / "junk.alc"))
+    assert r.returncode == 0 and "Chunks:" not in r.stdout and "  Width:       8" in r.stdout
+    # the reference's --quality is a u8: out-of-range values are an error, not a Python traceback
+    r = run("encode", str(tmp_path / "a.rgb"), "-W", "8", "-H", "8", "-f", "2", "-q", "300", "-o", str(tmp_path / "x.alc"))
+    assert r.returncode == 1 and r.stderr.startswith("error: ") and "Traceback" not in r.stderr
 
 
 @pytest.mark.gpu

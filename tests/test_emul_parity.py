@@ -113,3 +113,7 @@ def test_errors_and_abi(api):
 
 def test_shared_workspace_batch(api):
     parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5), (96, 4, 64)), n=3)
+
+
+def test_payload_arena_tight_and_overflowing(api):
+    parity.check_payload_arena(api)

@@ -270,12 +270,21 @@ def test_batch_api_device_and_host(api):
         batch.decode_host(chunks, [t.data_ptr() for t in h_out])
         for i in range(n):
             assert np.array_equal(h_out[i].numpy(), O.decode(refs[i]))
+        # decode_host reuses the batch's histogram / payload buffers: what the last encode left resident is gone, and the
+        # calls that would read it say so instead of returning another batch's data (include/alice_codec.h)
+        with pytest.raises(pkg.CodecError) as ei:
+            batch.get_chunk(0)
+        assert ei.value.kind == "InvalidBufferSize"
+        with pytest.raises(pkg.CodecError):
+            batch.decode_device([t.data_ptr() for t in d_out])
+        batch.encode_device([t.data_ptr() for t in d_in])          # ... until the next encode
+        assert batch.get_chunk(n - 1).to_bytes() == refs[n - 1]
         assert len(batch.timings()) == 8 and batch.device_bytes() > 0
         batch.close()
 
 
 def test_shared_workspace_batch(api):
-    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5), (256, 64, 64)), n=3)
+    parity.check_shared_workspace_batch(api, shapes=((20, 12, 6), (21, 13, 5), (256, 64, 64), (96, 4, 64)), n=3)
 
 
 def test_synth_on_device_matches_oracle_generators(api):
@@ -301,3 +310,7 @@ def test_determinism_and_idempotence(api):
     d1 = pkg.FrameDecoder(api=api).decode(ck)
     d2 = pkg.FrameDecoder(api=api).decode(ck)
     assert np.array_equal(d1, d2)
+
+
+def test_payload_arena_tight_and_overflowing(api):
+    parity.check_payload_arena(api)

@@ -63,6 +63,14 @@ SIGNATURES = {
     "alice_codec_wavelet2d_inverse": (cint, [u8, i32p, u32, u32]),
     "alice_codec_wavelet3d_forward": (cint, [u8, i32p, u32, u32, u32]),
     "alice_codec_wavelet3d_inverse": (cint, [u8, i32p, u32, u32, u32]),
+    "alice_codec_wavelet2d_device": (cint, [u8, cint, C.c_void_p, C.c_void_p, u32, u32, u32, C.c_void_p]),
+    "alice_codec_wavelet3d_device": (cint, [u8, cint, C.c_void_p, C.c_void_p, u32, u32, u32, C.c_void_p]),
+    "alice_codec_lossless_create": (vp, [u32, u32, u32, vp]),
+    "alice_codec_lossless_destroy": (None, [vp]),
+    "alice_codec_lossless_encode_device": (cint, [vp, C.c_void_p]),
+    "alice_codec_lossless_decode_device": (cint, [vp]),
+    "alice_codec_lossless_fetch": (cint, [vp, cint, cint, C.c_void_p, u64, u64p]),
+    "alice_codec_lossless_timings": (cint, [vp, C.POINTER(C.c_float)]),
     "alice_codec_quantize_buffer": (cint, [i32, i32, i32p, u64, i32p, u64]),
     "alice_codec_dequantize_buffer": (cint, [i32, i32p, u64, i32p, u64]),
     "alice_codec_fast_quantize_buffer": (cint, [i32, i32, i32p, u64, i32p, u64]),

@@ -583,3 +583,52 @@ class ChunkBatch:
 
     def device_bytes(self):
         return self._api.lib.alice_codec_batch_device_bytes(self._h)
+
+
+class LosslessSet:
+    """BASELINE config 4 on the device (alice_codec_lossless_*): the reference's lossless module (src/lossless.rs:
+    transform_2d / inverse_2d = Wavelet2D::cdf53) over a frame set, with the reference's symbol, histogram, table and rANS
+    stages per colour channel.  `d_rgb` is a device pointer (integer)."""
+
+    STAGES = {"coeffs": (0, np.int32), "symbols": (1, np.uint8), "hist": (2, np.uint32), "decoded": (3, np.uint8),
+              "inverse": (4, np.int32)}
+
+    def __init__(self, width, height, frames, stream: int = 0, api: Api | None = None):
+        self._api = api or default_api()
+        self.shape = (width, height, frames)
+        self.n = width * height * frames
+        self._h = self._api.lib.alice_codec_lossless_create(width, height, frames, C.c_void_p(stream))
+        if not self._h:
+            self._api._raise()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._api.lib.alice_codec_lossless_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def encode_device(self, d_rgb):
+        self._api._chk(self._api.lib.alice_codec_lossless_encode_device(self._h, C.c_void_p(int(d_rgb))))
+
+    def decode_device(self):
+        self._api._chk(self._api.lib.alice_codec_lossless_decode_device(self._h))
+
+    def fetch(self, what):
+        which, dt = self.STAGES[what]
+        count = 3 * 256 if what == "hist" else 3 * self.n
+        out = np.empty(count, dtype=dt)
+        n = C.c_uint64(0)
+        self._api._chk(self._api.lib.alice_codec_lossless_fetch(self._h, which, 0, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(n)))
+        return out.reshape(3, -1)
+
+    def stream(self, channel) -> bytes:
+        buf = np.empty(2 * self.n + 2048, dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._api._chk(self._api.lib.alice_codec_lossless_fetch(self._h, 5, channel, buf.ctypes.data_as(C.c_void_p), buf.nbytes, C.byref(n)))
+        return buf[:n.value].tobytes()
+
+    def timings(self):
+        ms = (C.c_float * 8)()
+        self._api._chk(self._api.lib.alice_codec_lossless_timings(self._h, ms))
+        return list(ms)

@@ -57,6 +57,44 @@ uint8_t *boxed_copy(const uint8_t *src, size_t len) {
     return p;
 }
 
+// wavelet.rs:392-438 / 441-484 (3-D), :292-340 (2-D), :133-176 (1-D) on device buffers A (data) and B (scratch of the same
+// size).  *result = the buffer that holds the transform afterwards: A, except for the fast 2-D path (one out-of-place pass).
+int wavelet_nd_device(uint8_t wavelet, bool inverse, int32_t *A, int32_t *B, uint64_t w, uint64_t h, uint64_t d, int ndim,
+                      cudaStream_t st, int32_t **result) {
+    *result = A;
+    if (wavelet_fast_eligible(A, B, (long long)w, (long long)h, (long long)d, ndim)) {
+        const size_t fs = (size_t)w * h;
+        if (ndim == 2) {               // d images, each transformed on its own
+            wavelet_xy_i32(wavelet, inverse, A, B, (int)w, (int)h, (long long)d, st);
+            *result = B;
+        } else if (!inverse) {
+            wavelet_xy_i32(wavelet, false, A, B, (int)w, (int)h, (long long)d, st);
+            wavelet_t_i32(wavelet, false, B, A, fs, (int)d, st);
+        } else {
+            wavelet_t_i32(wavelet, true, A, B, fs, (int)d, st);
+            wavelet_xy_i32(wavelet, true, B, A, (int)w, (int)h, (long long)d, st);
+        }
+        return kOk;
+    }
+    if (ndim == 2 && d != 1) {         // the step-by-step path transforms one image at a time
+        for (uint64_t t = 0; t < d; t++) {
+            lift_axis(A + t * w * h, B + t * w * h, wavelet, inverse, inverse ? 1 : 0, (long long)w, (long long)h, 1, st);
+            lift_axis(A + t * w * h, B + t * w * h, wavelet, inverse, inverse ? 0 : 1, (long long)w, (long long)h, 1, st);
+        }
+        return kOk;
+    }
+    if (!inverse) {
+        lift_axis(A, B, wavelet, false, 0, (long long)w, (long long)h, (long long)d, st);
+        if (ndim >= 2) lift_axis(A, B, wavelet, false, 1, (long long)w, (long long)h, (long long)d, st);
+        if (ndim >= 3) lift_axis(A, B, wavelet, false, 2, (long long)w, (long long)h, (long long)d, st);
+    } else {
+        if (ndim >= 3) lift_axis(A, B, wavelet, true, 2, (long long)w, (long long)h, (long long)d, st);
+        if (ndim >= 2) lift_axis(A, B, wavelet, true, 1, (long long)w, (long long)h, (long long)d, st);
+        lift_axis(A, B, wavelet, true, 0, (long long)w, (long long)h, (long long)d, st);
+    }
+    return kOk;
+}
+
 int wavelet_nd(uint8_t wavelet, bool inverse, int32_t *data, uint64_t w, uint64_t h, uint64_t d, int ndim) {
     if (!data) { set_error(kErrNull, "null data"); return kErrNull; }
     if (wavelet > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return kErrBitstream; }
@@ -69,18 +107,11 @@ int wavelet_nd(uint8_t wavelet, bool inverse, int32_t *data, uint64_t w, uint64_
     if (!a.alloc(n * 4) || !b.alloc(n * 4)) return kErrCuda;
     CU_CHECK_RC(cudaMemcpy(a.p, data, n * 4, cudaMemcpyHostToDevice));
     int32_t *A = a.as<int32_t>(), *B = b.as<int32_t>();
-    // wavelet.rs:392-438 / 441-484 (3-D), :292-340 (2-D), :133-176 (1-D)
-    if (!inverse) {
-        lift_axis(A, B, wavelet, false, 0, (long long)w, (long long)h, (long long)d, nullptr);
-        if (ndim >= 2) lift_axis(A, B, wavelet, false, 1, (long long)w, (long long)h, (long long)d, nullptr);
-        if (ndim >= 3) lift_axis(A, B, wavelet, false, 2, (long long)w, (long long)h, (long long)d, nullptr);
-    } else {
-        if (ndim >= 3) lift_axis(A, B, wavelet, true, 2, (long long)w, (long long)h, (long long)d, nullptr);
-        if (ndim >= 2) lift_axis(A, B, wavelet, true, 1, (long long)w, (long long)h, (long long)d, nullptr);
-        lift_axis(A, B, wavelet, true, 0, (long long)w, (long long)h, (long long)d, nullptr);
-    }
+    int32_t *res = A;
+    int rc = wavelet_nd_device(wavelet, inverse, A, B, w, h, d, ndim, nullptr, &res);
+    if (rc) return rc;
     CU_CHECK_RC(cudaGetLastError());
-    CU_CHECK_RC(cudaMemcpy(data, a.p, n * 4, cudaMemcpyDeviceToHost));
+    CU_CHECK_RC(cudaMemcpy(data, res, n * 4, cudaMemcpyDeviceToHost));
     return kOk;
 }
 
@@ -357,6 +388,46 @@ int alice_codec_wavelet3d_forward(uint8_t wv, int32_t *data, uint32_t w, uint32_
 int alice_codec_wavelet3d_inverse(uint8_t wv, int32_t *data, uint32_t w, uint32_t h, uint32_t d) {
     set_error(0, "");
     return wavelet_nd(wv, true, data, w, h, d, 3);
+}
+
+// Device-pointer forms of Wavelet2D / Wavelet3D (no host copies; asynchronous on `cuda_stream`).
+//   2-D: n_images images of w x h, out of place (d_src -> d_dst, the buffers must not overlap);
+//   3-D: one w x h x d volume, in place in d_data with a scratch volume d_tmp of the same size.
+int alice_codec_wavelet2d_device(uint8_t wv, int inverse, const int32_t *d_src, int32_t *d_dst, uint32_t w, uint32_t h,
+                                 uint32_t n_images, void *cuda_stream) {
+    set_error(0, "");
+    if (!d_src || !d_dst) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (wv > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return kErrBitstream; }
+    if (!cuda_ready()) return kErrCuda;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t n = (size_t)w * h * n_images;
+    if (n == 0) return kOk;
+    if (wavelet_fast_eligible(d_src, d_dst, w, h, n_images, 2)) {
+        wavelet_xy_i32(wv, inverse != 0, d_src, d_dst, (int)w, (int)h, (long long)n_images, st);
+    } else {
+        int32_t *tmp = (int32_t *)scratch_device(n * 4);
+        if (!tmp) { set_error(kErrCuda, "scratch allocation failed"); return kErrCuda; }
+        CU_CHECK_RC(cudaMemcpyAsync(d_dst, d_src, n * 4, cudaMemcpyDeviceToDevice, st));
+        int32_t *res = nullptr;
+        int rc = wavelet_nd_device(wv, inverse != 0, d_dst, tmp, w, h, n_images, 2, st, &res);
+        if (rc) return rc;
+        if (res != d_dst) CU_CHECK_RC(cudaMemcpyAsync(d_dst, res, n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CU_CHECK_RC(cudaGetLastError());
+    return kOk;
+}
+int alice_codec_wavelet3d_device(uint8_t wv, int inverse, int32_t *d_data, int32_t *d_tmp, uint32_t w, uint32_t h, uint32_t d,
+                                 void *cuda_stream) {
+    set_error(0, "");
+    if (!d_data || !d_tmp) { set_error(kErrNull, "null argument"); return kErrNull; }
+    if (wv > 2) { set_error(kErrBitstream, "unknown wavelet type byte"); return kErrBitstream; }
+    if (!cuda_ready()) return kErrCuda;
+    if ((size_t)w * h * d == 0) return kOk;
+    int32_t *res = nullptr;
+    int rc = wavelet_nd_device(wv, inverse != 0, d_data, d_tmp, w, h, d, 3, (cudaStream_t)cuda_stream, &res);
+    if (rc) return rc;
+    CU_CHECK_RC(cudaGetLastError());
+    return kOk;
 }
 
 namespace {
@@ -979,16 +1050,21 @@ int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chun
     Engine *e = b->eng;
     if (n > e->cap_chunks()) { set_error(kErrBufferSize, "batch larger than capacity"); return kErrBufferSize; }
     const size_t bytes = (size_t)e->dims().n_pixels * 3;
+    // shared-workspace batches: chunk i's symbol planes go to staging buffer i, its RGB to staging buffer i + 1 (the
+    // back-end runs the chunks in descending order, so that buffer's planes have been consumed: Engine::run_backend)
+    const bool shared = e->shared_workspace();
     std::vector<const Chunk *> cks(n);
     b->stage_ptrs.resize(n);
+    b->work_ptrs.resize(n);
     for (uint32_t i = 0; i < n; i++) {
         if (!chunks[i]) { set_error(kErrNull, "null chunk"); return kErrNull; }
         cks[i] = &chunks[i]->c;
-        uint8_t *s = e->rgb_stage(i);
-        if (!s) return kErrCuda;
+        uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
+        if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
         b->stage_ptrs[i] = s;
+        b->work_ptrs[i] = shared ? e->rgb_stage(i) : nullptr;
     }
-    int rc = e->decode_chunks(cks.data(), n, b->stage_ptrs.data());
+    int rc = e->decode_chunks(cks.data(), n, b->stage_ptrs.data(), shared ? b->work_ptrs.data() : nullptr);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++)
         CU_CHECK_RC(cudaMemcpyAsync(h_rgb_out[i], b->stage_ptrs[i], bytes, cudaMemcpyDeviceToHost, e->stream()));

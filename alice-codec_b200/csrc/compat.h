@@ -113,6 +113,7 @@ __device__ __forceinline__ void mbar_wait(mbar_t *b, unsigned parity) {
 #endif
 
 namespace alice {
+template <bool V> struct BoolTag { static constexpr bool value = V; };   // compile-time flag passed to generic lambdas
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 constexpr unsigned kFullMask = 0xffffffffu;
 }  // namespace alice

@@ -237,6 +237,8 @@ Engine::Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap, cudaStr
     a = a && dev_alloc(d_enc_jobs_, S * sizeof(RansEncJob), dev_bytes_);
     a = a && dev_alloc(d_dec_jobs_, S * sizeof(RansDecJob), dev_bytes_);
     a = a && dev_alloc(d_fwd_jobs_, (size_t)cap_ * sizeof(FwdFusedJob), dev_bytes_);
+    a = a && dev_alloc(d_inv_jobs_, (size_t)cap_ * sizeof(InvFusedJob), dev_bytes_);
+    a = a && cudaMallocHost((void **)&h_inv_jobs_, (size_t)cap_ * sizeof(InvFusedJob)) == cudaSuccess;
     a = a && cudaMallocHost((void **)&h_fwd_jobs_, (size_t)cap_ * sizeof(FwdFusedJob)) == cudaSuccess;
     a = a && dev_alloc(d_results_, S * 2 * sizeof(unsigned long long), dev_bytes_);
     a = a && cudaMallocHost((void **)&h_results_, S * 2 * sizeof(unsigned long long)) == cudaSuccess;
@@ -267,7 +269,9 @@ Engine::~Engine() {
     if (h_enc_jobs_) cudaFreeHost(h_enc_jobs_);
     if (h_dec_jobs_) cudaFreeHost(h_dec_jobs_);
     if (h_fwd_jobs_) cudaFreeHost(h_fwd_jobs_);
+    if (h_inv_jobs_) cudaFreeHost(h_inv_jobs_);
     cudaFree(d_fwd_jobs_);
+    cudaFree(d_inv_jobs_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     if (st_ && own_stream_) cudaStreamDestroy(st_);
     cudaGetLastError();
@@ -485,6 +489,45 @@ int Engine::fetch_chunks(uint32_t n, Chunk *const *out) {
     return kOk;
 }
 
+// Back-end of n chunks whose symbol planes are in sym_ptr_[c]: RGB into d_rgb_out[c].  Chunks of the fused kernel's shape
+// whose headers stay within its arithmetic bound take k_inv_fused, which reads symbols and writes RGB in the same launch:
+//   * engine-owned symbol planes, one header for the whole batch: one launch;
+//   * caller-provided workspaces (shared-workspace batches): one launch per chunk in DESCENDING index order, so the output
+//     of chunk i may be the workspace of any chunk j > i (already consumed); an output that overlaps its own chunk's
+//     symbol planes falls back to the two-kernel path, which finishes reading the planes before it writes RGB.
+int Engine::run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_rgb_out) {
+    const size_t N = (size_t)d_.padded;
+    auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
+    const int n_sms = device_sm_count();
+    std::vector<char> fused(n, 0);
+    bool any = false, uniform = true;
+    const char *hook = getenv("ALICE_INV_FUSED");   // measurement hook (tools/frontend_time.py), removed once decided
+    for (uint32_t c = 0; c < n; c++) {
+        fused[c] = !(hook && hook[0] == '0') && inverse_fused_eligible(sym_ptr_[c], d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, hdr[c].steps) &&
+                   !overlaps(sym_ptr_[c], 3 * N, d_rgb_out[c], 3 * (size_t)d_.n_pixels);
+        any = any || fused[c];
+        uniform = uniform && fused[c] && hdr[c].wavelet == hdr[0].wavelet && hdr[c].steps[0] == hdr[0].steps[0] &&
+                  hdr[c].steps[1] == hdr[0].steps[1] && hdr[c].steps[2] == hdr[0].steps[2];
+    }
+    if (any) {
+        for (uint32_t c = 0; c < n; c++) h_inv_jobs_[c] = InvFusedJob{sym_ptr_[c], d_rgb_out[c]};
+        CU_TRY(cudaMemcpyAsync(d_inv_jobs_, h_inv_jobs_, n * sizeof(InvFusedJob), cudaMemcpyHostToDevice, st_));
+    }
+    if (uniform && !shared_ws_) {
+        inverse_backend_fused(hdr[0].wavelet, d_inv_jobs_, (int)n, (int)d_.w, (int)d_.h, hdr[0].steps, n_sms, st_);
+        return kOk;
+    }
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t c = shared_ws_ ? n - 1 - k : k;
+        if (fused[c])
+            inverse_backend_fused(hdr[c].wavelet, d_inv_jobs_ + c, 1, (int)d_.w, (int)d_.h, hdr[c].steps, n_sms, st_);
+        else
+            inverse_backend(hdr[c].wavelet, sym_ptr_[c], reinterpret_cast<int32_t *>(d_scratch_), d_rgb_out[c], (int)d_.w,
+                            (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, hdr[c].steps, st_);
+    }
+    return kOk;
+}
+
 int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     if (n > last_n) { set_error(kErrBufferSize, "decode_device: more chunks than the last encode"); return kErrBufferSize; }
     const size_t N = (size_t)d_.padded;
@@ -501,10 +544,12 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
     rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
     CU_TRY(cudaEventRecord(ev_[6], st_));
-    const int steps[3] = {last_step, last_step, last_step};
-    for (uint32_t c = 0; c < n; c++)
-        inverse_backend(last_wavelet, sym_ptr_[c], reinterpret_cast<int32_t *>(d_scratch_),
-                        d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
+    {
+        std::vector<BackendHeader> hdr(n);
+        for (uint32_t c = 0; c < n; c++) hdr[c] = BackendHeader{last_wavelet, {last_step, last_step, last_step}};
+        int rc = run_backend(n, hdr.data(), d_rgb_out);
+        if (rc) return rc;
+    }
     CU_TRY(cudaEventRecord(ev_[7], st_));
     CU_TRY(cudaStreamSynchronize(st_));
     CU_TRY(cudaGetLastError());
@@ -514,15 +559,15 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     return kOk;
 }
 
-int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out) {
+int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work) {
     if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
     // This call reuses the histogram, table, payload and overflow buffers of the last encode: whatever encode_device left
     // resident is gone afterwards (fetch_chunk / decode_device_resident then report "out of range" instead of returning
     // another batch's data).
     last_n = 0;
     for (size_t s = 0; s < stream_base_.size(); s++) { stream_base_[s] = nullptr; stream_len_[s] = 0; stream_off_[s] = 0; }
-    if (shared_ws_)   // the symbol planes of chunk i live in its output buffer (>= workspace_bytes()) until the last kernel
-        for (uint32_t i = 0; i < n; i++) sym_ptr_[i] = d_rgb_out[i];
+    if (shared_ws_)   // the symbol planes of chunk i live in its workspace, by default its output buffer (>= workspace_bytes())
+        for (uint32_t i = 0; i < n; i++) sym_ptr_[i] = d_work ? d_work[i] : d_rgb_out[i];
     const size_t N = (size_t)d_.padded;
     const uint32_t S = n * 3;
     // validation, in the reference's order (pipeline.rs:562-579)
@@ -589,11 +634,14 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
     CU_TRY(cudaEventRecord(ev_[5], st_));
     rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
     CU_TRY(cudaEventRecord(ev_[6], st_));
-    for (uint32_t i = 0; i < n; i++) {
-        const Chunk &ck = *chunks[i];
-        const int steps[3] = {ck.ch[0].quant_step, ck.ch[1].quant_step, ck.ch[2].quant_step};
-        inverse_backend(ck.wavelet, sym_ptr_[i], reinterpret_cast<int32_t *>(d_scratch_),
-                        d_rgb_out[i], (int)d_.w, (int)d_.h, (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, steps, st_);
+    {
+        std::vector<BackendHeader> hdr(n);
+        for (uint32_t i = 0; i < n; i++) {
+            const Chunk &ck = *chunks[i];
+            hdr[i] = BackendHeader{ck.wavelet, {ck.ch[0].quant_step, ck.ch[1].quant_step, ck.ch[2].quant_step}};
+        }
+        int rc = run_backend(n, hdr.data(), d_rgb_out);
+        if (rc) return rc;
     }
     CU_TRY(cudaEventRecord(ev_[7], st_));
     CU_TRY(cudaStreamSynchronize(st_));

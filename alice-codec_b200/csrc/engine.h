@@ -106,7 +106,9 @@ public:
     // Decode the payloads the last encode_device left on the device.
     int decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n);
     // Upload n host chunks (headers + payload) and decode them into device buffers d_rgb_out[i].
-    int decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out);
+    // d_work (shared-workspace engines): where chunk i's symbol planes go; default = its output buffer, which keeps the
+    // chunk on the two-kernel back-end (see run_backend for the aliasing rules of the fused one)
+    int decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work = nullptr);
 
     // staging buffers for host-pointer entry points
     uint8_t *rgb_stage(uint32_t slot);          // device buffer of 3*n_pixels bytes, slot in [0, n_stage)
@@ -119,6 +121,8 @@ public:
 
 private:
     int run_rans_encode(uint32_t n);
+    struct BackendHeader { uint8_t wavelet; int steps[3]; };   // what the back-end needs from a chunk's headers
+    int run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_rgb_out);
     int fetch_enqueue(uint32_t i, Chunk &out, bool &direct);
     Dims d_;
     uint32_t cap_ = 0;
@@ -139,6 +143,7 @@ private:
     RansEncJob *d_enc_jobs_ = nullptr;
     RansDecJob *d_dec_jobs_ = nullptr;
     FwdFusedJob *d_fwd_jobs_ = nullptr, *h_fwd_jobs_ = nullptr;   // per chunk: RGB, symbols, histogram (fused front-end)
+    InvFusedJob *d_inv_jobs_ = nullptr, *h_inv_jobs_ = nullptr;   // per chunk: symbols, RGB (fused back-end)
     unsigned long long *d_results_ = nullptr;  // [cap*3][2]
     std::vector<uint8_t *> rgb_stage_;
     std::vector<uint8_t *> overflow_bufs_;     // per stream, full-size retry buffers (rare)

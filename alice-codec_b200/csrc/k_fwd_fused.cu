@@ -41,8 +41,6 @@ constexpr int kFsRowPitch = 224;      // ring pitch: two rows = 112 words = 16 b
 constexpr int kFsLines = 3 * 2 * kFsCols;   // 336 temporal lines per row pair: channel x (low / high row) x column
 constexpr int kFsFrameI16 = 352;      // t-buffer frame stride in i16 (704 bytes = 176 words = 16 banks mod 32)
 
-template <bool V> struct IntTag { static constexpr bool value = V; };
-
 template <int WT> struct FusedGeom {
     static constexpr int NST = WaveletTraits<WT>::NST;
     static constexpr int NFR = 32 + 2 * NST;          // frames per block: half the temporal axis + NST halo pairs
@@ -286,8 +284,8 @@ k_fwd_fused(const FwdFusedJob *__restrict__ jobs, int w, int h, int n_strips, in
         n_acc = 0;
     };
     static_assert(Q > NST, "the warm-up steps must fall into the first group");
-    if (n_groups > 0) run_group(0, IntTag<true>());
-    for (int g = 1; g < n_groups; g++) run_group(g, IntTag<false>());
+    if (n_groups > 0) run_group(0, BoolTag<true>());
+    for (int g = 1; g < n_groups; g++) run_group(g, BoolTag<false>());
     if (je == halfy && k > 0) {   // bottom of the image: the last NST row pairs come out of the flush
 #pragma unroll
         for (int which = 0; which < NST; which++) {

@@ -351,7 +351,7 @@ k_inv_yx(const void *__restrict__ coef_v, uint8_t *__restrict__ rgb, int w, int 
 // axis, neighbour sums (a+b) 4.549 / 2.5 / 3.0 (CDF 9/7 / CDF 5/3 / Haar).  With A = 15000: the i16 hand-off after
 // the t pass holds <= 2.0 A = 30000; the largest product in the x pass is 4.549 * 1.6663^2 A * 6497 = 1.2e9
 // (9/7), 3.0 * 4 A * 4096 = 7.4e8 (Haar) < 2^31.
-constexpr long long kNarrowMaxCoef = 15000;
+constexpr long long kNarrowMaxCoef = kInvNarrowMaxCoef;   // kernels.h
 
 template <int WT, bool WIDE>
 static void launch_inv(const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f, int pw, int ph,

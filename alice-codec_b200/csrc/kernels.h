@@ -24,6 +24,17 @@ bool forward_fused_eligible(const uint8_t *d_rgb, int w, int h, int f);
 void forward_frontend_fused(int wavelet, const FwdFusedJob *d_jobs, int n_jobs, bool dump, unsigned *d_hist_base, int w, int h,
                             int step, int n_sms, cudaStream_t st);
 int device_sm_count();       // multiprocessors of the current device (cached)
+// The fused back-end (k_inv_fused.cu): the same shapes as the fused front-end, and quantiser steps within the 32-bit
+// lifting bound (128 * |step| <= kInvNarrowMaxCoef, derived in k_inverse.cu).  The kernel reads symbols and writes RGB
+// in the same launch: a chunk's RGB output must not overlap the symbol planes of any chunk of the same launch.
+constexpr long long kInvNarrowMaxCoef = 15000;
+struct InvFusedJob {
+    const uint8_t *symbols;  // [3][64][h][w]
+    uint8_t *rgb;            // [64][h][w][3]
+};
+bool inverse_fused_eligible(const uint8_t *d_symbols, const uint8_t *d_rgb, int w, int h, int f, const int steps[3]);
+void inverse_backend_fused(int wavelet, const InvFusedJob *d_jobs, int n_jobs, int w, int h, const int steps[3], int n_sms,
+                           cudaStream_t st);
 // symbols: u8 [3][pf*ph*pw]; coef: i32 [3][f][ph][pw] scratch; steps[3] = per-channel quant_step from the header
 void inverse_backend(int wavelet, const uint8_t *d_symbols, int32_t *d_coef, uint8_t *d_rgb, int w, int h, int f,
                      int pw, int ph, int pf, const int steps[3], cudaStream_t st);
@@ -78,6 +89,13 @@ void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecA
 // ---- generic element-wise / line kernels behind the public stage API (k_generic.cu) -----
 void lift_axis(int32_t *d_data, int32_t *d_tmp, int wavelet, bool inverse, int axis, long long w, long long h,
                long long d, cudaStream_t st);  // one 1-D transform along `axis` (0=x,1=y,2=t) of every line
+// fast per-pass kernels for volumes with w % 4 == 0 and even transformed dimensions (k_wavelet_i32.cu), out of place:
+//   wavelet_xy_i32: the 2-D transform (or its inverse) of each of n_frames images of w x h
+//   wavelet_t_i32 : the temporal transform (or its inverse) of a w*h = frame_sz by d volume
+bool wavelet_fast_eligible(const int32_t *a, const int32_t *b, long long w, long long h, long long d, int ndim);
+void wavelet_xy_i32(int wavelet, bool inverse, const int32_t *d_src, int32_t *d_dst, int w, int h, long long n_frames,
+                    cudaStream_t st);
+void wavelet_t_i32(int wavelet, bool inverse, const int32_t *d_src, int32_t *d_dst, size_t frame_sz, int d, cudaStream_t st);
 void rgb_to_ycocg(const uint8_t *d_rgb, int16_t *d_y, int16_t *d_co, int16_t *d_cg, size_t n, cudaStream_t st);
 void ycocg_to_rgb(const int16_t *d_y, const int16_t *d_co, const int16_t *d_cg, uint8_t *d_rgb, size_t n,
                   cudaStream_t st);

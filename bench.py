@@ -553,9 +553,7 @@ def run_e2e(args, wl, pkg, api, B, seeds, local, rank, world, barrier, golden, p
     e2e_ok = None
     if rank == 0 and golden and keep[0] is not None:    # outside the timed region: chunk 0 of the last step, decoded alone
         alc_ok = sha(keep[0].to_bytes()) == golden["sha256_alc"]
-        one = pkg.ChunkBatch(wl["q"], wl["wavelet"], W, H, F, 1, stream=streams[0].cuda_stream, api=api, shared_workspace=True)
-        one.decode_host([keep[0]], [h_out[0][0].data_ptr()])
-        one.close()
+        batches[0].decode_host([keep[0]], [h_out[0][0].data_ptr()])
         e2e_ok = alc_ok and sha(h_out[0][0].numpy().tobytes()) == golden["sha256_decoded"]
     keep[0] = None
     res = {"value": round(Be * F * world * steps / dt, 2), "unit": "frames/s",

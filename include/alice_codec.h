@@ -170,6 +170,32 @@ EncodedChunk *alice_codec_encode_stages(const FrameEncoder *encoder, const uint8
                                         uint8_t *symbols_out);
 uint8_t *alice_codec_decode_stages(const EncodedChunk *chunk, uint64_t *out_len, uint8_t *symbols_out);
 
+/* Wavelet2D / Wavelet3D on DEVICE buffers (same arithmetic as the host-pointer entry points; asynchronous on cuda_stream).
+ * 2-D: n_images images of width x height, out of place (d_src and d_dst must not overlap) — LosslessEncoder::transform_2d /
+ * inverse_2d (lossless.rs:45-54) over a stack of frames is wavelet 0 (CDF 5/3).  3-D: in place in d_data, d_tmp = scratch of
+ * the same size.  Volumes with width % 4 == 0 and even height (and depth) take the one-pass-per-plane / per-line kernels
+ * (16 B per sample of memory traffic for a 3-D transform); other shapes the step-by-step path. */
+int alice_codec_wavelet2d_device(uint8_t wavelet, int inverse, const int32_t *d_src, int32_t *d_dst, uint32_t width,
+                                 uint32_t height, uint32_t n_images, void *cuda_stream);
+int alice_codec_wavelet3d_device(uint8_t wavelet, int inverse, int32_t *d_data, int32_t *d_tmp, uint32_t width,
+                                 uint32_t height, uint32_t depth, void *cuda_stream);
+
+/* ---- the lossless module over a frame set, on the device (BASELINE config 4; src/lossless.rs + the reference's own
+ * entropy stages): per colour channel of a width x height x frames RGB volume, rgb_bytes_to_ycocg_r -> i32 planes ->
+ * LosslessEncoder::transform_2d of every frame -> to_symbols (step 1, wrapping) -> build_histogram ->
+ * FrequencyTable::from_histogram -> RansEncoder (one stream per channel) ; decode = RansDecoder + inverse_2d of the
+ * coefficients.  fetch copies a stage buffer to the host for parity checks: which = 0 coefficients (i32 [3][n]),
+ * 1 symbols (u8 [3][n]), 2 histograms (u32 [3][256]), 3 decoded symbols, 4 inverse-transformed planes (i32 [3][n]),
+ * 5 the rANS stream of `channel`.  timings: [0] colour, [1] 2-D forward, [2] symbols + histograms + tables,
+ * [3] rANS encode, [4] rANS decode, [5] 2-D inverse (ms, CUDA events). */
+typedef struct AliceLossless AliceLossless;
+AliceLossless *alice_codec_lossless_create(uint32_t width, uint32_t height, uint32_t frames, void *cuda_stream);
+void alice_codec_lossless_destroy(AliceLossless *l);
+int alice_codec_lossless_encode_device(AliceLossless *l, const uint8_t *d_rgb);
+int alice_codec_lossless_decode_device(AliceLossless *l);
+int alice_codec_lossless_fetch(AliceLossless *l, int which, int channel, void *host_out, uint64_t cap, uint64_t *out_len);
+int alice_codec_lossless_timings(AliceLossless *l, float *ms8);
+
 /* ---- batch / device-pointer API: many independent chunks of one shape in flight ---- */
 typedef struct AliceBatch AliceBatch;
 /* cuda_stream: a cudaStream_t (may be null = the legacy default stream) on which all work is issued */

@@ -79,6 +79,15 @@ def check_wavelet_api(api, rng, shapes_1d, shapes_2d, shapes_3d, amplitude=1 << 
                                   O.wavelet3d_inverse(wv, fw, w, h, d))
 
 
+def check_wavelet_fast_path(api, shapes_2d=((8, 2), (16, 10), (128, 6), (244, 8), (480, 34)),
+                            shapes_3d=((8, 2, 2), (16, 6, 4), (124, 8, 6), (256, 4, 64), (132, 36, 10))):
+    """Shapes with w % 4 == 0 and even h (and d) take the per-pass kernels of k_wavelet_i32.cu (strips with and without
+    interior lanes, several row segments, full-range i32 data for the i64 lifting product)."""
+    rng = np.random.default_rng(11)
+    check_wavelet_api(api, rng, [], shapes_2d, shapes_3d, amplitude=1 << 20)
+    check_wavelet_api(api, rng, [], shapes_2d[:3], shapes_3d[:3], amplitude=(1 << 31) - 1)
+
+
 def check_wavelet_extremes(api):
     """i32 wrap-around and the i64 lifting product (wavelet.rs:193-195): full-range inputs."""
     rng = np.random.default_rng(7)
@@ -478,3 +487,44 @@ def check_payload_arena(api, w=48, h=20, f=8, n=4):
             for i in range(n):
                 assert np.array_equal(h_out[i].numpy(), outs[i]), (q, wv, budget, i)
             batch.close()
+
+
+def lossless_oracle(rgb, w, h, f):
+    """BASELINE config 4 on the oracle (tests/golden/make_golden.py::lossless_case), every stage returned"""
+    planes = O.rgb_bytes_to_ycocg_r(rgb)
+    fs = w * h
+    out = {"coeffs": [], "symbols": [], "hist": [], "streams": [], "decoded": [], "inverse": []}
+    for p in planes:
+        co = np.empty(fs * f, dtype=np.int32)
+        inv = np.empty(fs * f, dtype=np.int32)
+        for t in range(f):
+            fw = O.wavelet2d_forward(0, p[t * fs:(t + 1) * fs].astype(np.int32), w, h)
+            co[t * fs:(t + 1) * fs] = fw
+            inv[t * fs:(t + 1) * fs] = O.wavelet2d_inverse(0, fw, w, h)
+        sy = O.to_symbols(co)
+        hist = O.build_histogram(sy)
+        table = O.freq_table_from_histogram(hist)
+        stream = O.rans_encode(sy, table)
+        out["coeffs"].append(co); out["symbols"].append(sy); out["hist"].append(np.asarray(hist, dtype=np.uint32))
+        out["streams"].append(stream); out["decoded"].append(O.rans_decode(stream, sy.size, table)); out["inverse"].append(inv)
+    return out
+
+
+def check_lossless_set(api, shapes=((16, 6, 4), (21, 9, 3), (128, 8, 6))):
+    """alice_codec_lossless_* against the oracle's stages (fast 2-D kernels and the step-by-step path)"""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"        # the emulator treats host memory as device memory
+    for (w, h, f) in shapes:
+        rgb = O.generate(O.G1, w, h, f)
+        ref = lossless_oracle(rgb, w, h, f)
+        d_rgb = torch.from_numpy(rgb.copy()).to(dev)
+        ls = pkg.LosslessSet(w, h, f, api=api)
+        ls.encode_device(d_rgb.data_ptr())
+        ls.decode_device()
+        for what in ("coeffs", "symbols", "hist", "decoded", "inverse"):
+            got = ls.fetch(what)
+            for c in range(3):
+                assert np.array_equal(got[c], ref[what][c]), (w, h, f, what, c)
+        for c in range(3):
+            assert ls.stream(c) == ref["streams"][c], (w, h, f, c)
+        ls.close()

@@ -117,3 +117,11 @@ def test_shared_workspace_batch(api):
 
 def test_payload_arena_tight_and_overflowing(api):
     parity.check_payload_arena(api)
+
+
+def test_wavelet_api_fast_path(api):
+    parity.check_wavelet_fast_path(api)
+
+
+def test_lossless_set(api):
+    parity.check_lossless_set(api)

@@ -112,13 +112,13 @@ def test_fullsize_odd_and_noise(api):
     _fullsize(api, "noise_cdf53_q90_1080p8", want_coeffs=True)
 
 
-def test_fullsize_config5_two_4k_chunks_through_the_batch_api(api):
-    """BASELINE config 5 (3840x2160x512 = 8 chunks of 64 frames, CDF 9/7 q=80, chunk c = G1 seed + c): two of the
+def test_fullsize_config5_all_eight_4k_chunks_through_the_batch_api(api):
+    """BASELINE config 5 (3840x2160x512 = 8 chunks of 64 frames, CDF 9/7 q=80, chunk c = G1 seed + c): all eight
     chunks in flight through the batch API, .alc and decoded RGB against the oracle digests."""
     import ctypes as C
     import torch
     g = json.load(open(GOLDEN_PATH))
-    names = ["cfg5_cdf97_q80_4k64_chunk0", "cfg5_cdf97_q80_4k64_chunk1"]
+    names = [f"cfg5_cdf97_q80_4k64_chunk{c}" for c in range(8)]
     w, h, f = 3840, 2160, 64
     st = torch.cuda.current_stream()
     d_in = [torch.empty(w * h * f * 3, dtype=torch.uint8, device="cuda") for _ in names]
@@ -128,7 +128,8 @@ def test_fullsize_config5_two_4k_chunks_through_the_batch_api(api):
     batch = pkg.ChunkBatch(80, "cdf97", w, h, f, len(names), stream=st.cuda_stream, api=api)
     batch.encode_device([t.data_ptr() for t in d_in])
     for i, nm in enumerate(names):
-        assert sha(d_in[i].cpu().numpy().tobytes()) == g[nm]["sha256_rgb_in"]
+        if i in (0, 7):
+            assert sha(d_in[i].cpu().numpy().tobytes()) == g[nm]["sha256_rgb_in"]
         alc = batch.get_chunk(i).to_bytes()
         assert len(alc) == g[nm]["alc_len"]
         assert sha(alc) == g[nm]["sha256_alc"], f"{nm}: .alc differs from the oracle digest"
@@ -314,3 +315,35 @@ def test_determinism_and_idempotence(api):
 
 def test_payload_arena_tight_and_overflowing(api):
     parity.check_payload_arena(api)
+
+
+def test_wavelet_api_fast_path(api):
+    parity.check_wavelet_fast_path(api)
+
+
+def test_lossless_set(api):
+    parity.check_lossless_set(api)
+
+
+def test_fullsize_config4_lossless_1080p64(api):
+    """BASELINE config 4 at full size: every stage of the lossless frame-set pipeline against the oracle digests."""
+    import ctypes as C
+    import torch
+    g = json.load(open(GOLDEN_PATH))["cfg4_lossless_1080p64"]
+    w, h, f = g["w"], g["h"], g["f"]
+    st = torch.cuda.current_stream()
+    d_rgb = torch.empty(w * h * f * 3, dtype=torch.uint8, device="cuda")
+    api._chk(api.lib.alice_codec_synth_rgb_device(g["kind"], g["seed"], w, h, f, C.c_void_p(d_rgb.data_ptr()), C.c_void_p(st.cuda_stream)))
+    assert sha(d_rgb.cpu().numpy().tobytes()) == g["sha256_rgb_in"]
+    ls = pkg.LosslessSet(w, h, f, stream=st.cuda_stream, api=api)
+    ls.encode_device(d_rgb.data_ptr())
+    ls.decode_device()
+    for what, key in (("coeffs", "sha256_coeffs"), ("symbols", "sha256_symbols"), ("hist", "sha256_hist"),
+                      ("decoded", "sha256_decoded_symbols"), ("inverse", "sha256_inverse")):
+        got = ls.fetch(what)
+        for c in range(3):
+            assert sha(got[c].tobytes()) == g[key][c], f"{what} of channel {c} differs from the oracle digest"
+    for c in range(3):
+        s = ls.stream(c)
+        assert len(s) == g["stream_lens"][c] and sha(s) == g["sha256_streams"][c], f"rANS stream {c}"
+    ls.close()

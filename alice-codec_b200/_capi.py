@@ -101,6 +101,9 @@ SIGNATURES = {
     "alice_codec_batch_decode_device": (cint, [vp, C.POINTER(vp), u32]),
     "alice_codec_batch_encode_host": (cint, [vp, C.POINTER(vp), u32, C.POINTER(vp)]),
     "alice_codec_batch_decode_host": (cint, [vp, C.POINTER(vp), u32, C.POINTER(vp)]),
+    "alice_codec_batch_submit_host": (cint, [vp, u32, vp]),
+    "alice_codec_batch_collect": (cint, [vp, u32, C.POINTER(vp)]),
+    "alice_codec_batch_sync": (cint, [vp]),
     "alice_codec_batch_get_chunk": (vp, [vp, u32]),
     "alice_codec_batch_timings": (cint, [vp, C.POINTER(C.c_float)]),
     "alice_codec_batch_device_bytes": (u64, [vp]),

@@ -564,6 +564,18 @@ class ChunkBatch:
         self._api._chk(self._api.lib.alice_codec_batch_encode_host(self._h, arr, n, out))
         return [EncodedChunk(C.c_void_p(out[i]), self._api) for i in range(n)]
 
+    def submit_host(self, i, h_rgb_ptr):
+        """chunk-at-a-time encode: enqueue the copy and the front-end of chunk i (submit 0, 1, ... in order)"""
+        self._api._chk(self._api.lib.alice_codec_batch_submit_host(self._h, i, C.c_void_p(int(h_rgb_ptr))))
+
+    def sync(self):
+        self._api._chk(self._api.lib.alice_codec_batch_sync(self._h))
+
+    def collect(self, n):
+        out = (C.c_void_p * n)()
+        self._api._chk(self._api.lib.alice_codec_batch_collect(self._h, n, out))
+        return [EncodedChunk(C.c_void_p(out[i]), self._api) for i in range(n)]
+
     def decode_host(self, chunks, h_rgb_out_ptrs):
         n = len(chunks)
         cks = (C.c_void_p * n)(*[c._h for c in chunks])

@@ -1043,6 +1043,44 @@ int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, ui
     }
     return kOk;
 }
+// Chunk-at-a-time form of alice_codec_batch_encode_host: submit chunk 0, 1, ... as they arrive (the host -> device copy
+// and the front-end of that chunk are enqueued and the call returns at once), then collect.  The host does not have to
+// hold all chunks at once: a pinned host buffer may be reused as soon as its copy has completed (alice_codec_batch_sync).
+int alice_codec_batch_submit_host(AliceBatch *b, uint32_t i, const uint8_t *h_rgb) {
+    set_error(0, "");
+    if (!b || !h_rgb) { set_error(kErrNull, "null argument"); return kErrNull; }
+    Engine *e = b->eng;
+    if (i >= e->cap_chunks()) { set_error(kErrBufferSize, "chunk index beyond the batch capacity"); return kErrBufferSize; }
+    const size_t bytes = (size_t)e->dims().n_pixels * 3;
+    const bool shared = e->shared_workspace();
+    if (i == 0) {
+        int rc = e->encode_begin(b->quality, b->wavelet);
+        if (rc) return rc;
+    }
+    uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
+    if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
+    CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb, bytes, cudaMemcpyHostToDevice, e->stream()));
+    return e->encode_submit(i, s, shared ? e->rgb_stage(i) : nullptr);
+}
+int alice_codec_batch_collect(AliceBatch *b, uint32_t n, EncodedChunk **out_chunks) {
+    set_error(0, "");
+    if (!b || !out_chunks) { set_error(kErrNull, "null argument"); return kErrNull; }
+    Engine *e = b->eng;
+    int rc = e->encode_finish(n);
+    if (rc) return rc;
+    std::vector<Chunk *> cks(n);
+    for (uint32_t i = 0; i < n; i++) {
+        out_chunks[i] = new (std::nothrow) EncodedChunk();
+        if (!out_chunks[i]) { rc = kErrCuda; set_error(kErrCuda, "host allocation failed"); }
+        else cks[i] = &out_chunks[i]->c;
+    }
+    if (!rc) rc = e->fetch_chunks(n, cks.data());
+    if (rc) {
+        for (uint32_t k = 0; k < n; k++) { delete out_chunks[k]; out_chunks[k] = nullptr; }
+        return rc;
+    }
+    return kOk;
+}
 int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chunks, uint32_t n,
                                   uint8_t *const *h_rgb_out) {
     set_error(0, "");
@@ -1069,6 +1107,12 @@ int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chun
     for (uint32_t i = 0; i < n; i++)
         CU_CHECK_RC(cudaMemcpyAsync(h_rgb_out[i], b->stage_ptrs[i], bytes, cudaMemcpyDeviceToHost, e->stream()));
     CU_CHECK_RC(cudaStreamSynchronize(e->stream()));
+    return kOk;
+}
+int alice_codec_batch_sync(AliceBatch *b) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    CU_CHECK_RC(cudaStreamSynchronize(b->eng->stream()));
     return kOk;
 }
 int alice_codec_batch_timings(AliceBatch *b, float *ms8) {

@@ -424,6 +424,53 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
 }
 
 // headers of chunk i + the device->host copies of its payload, enqueued on the engine's stream (no synchronisation)
+// ---- chunk-at-a-time encode: encode_begin, then encode_submit(c) for c = 0, 1, ... in order (each enqueues the front-end of
+// one chunk and returns at once), then encode_finish(n): tables, all 3n rANS streams, one synchronisation.
+int Engine::encode_begin(uint8_t quality, uint8_t wavelet) {
+    last_wavelet = wavelet;
+    last_step = quality_to_step(quality);
+    last_n = 0;
+    submitted_ = 0;
+    CU_TRY(cudaEventRecord(ev_[0], st_));
+    return kOk;
+}
+int Engine::encode_submit(uint32_t c, const uint8_t *d_rgb, uint8_t *d_work) {
+    if (c >= cap_ || c != submitted_) { set_error(kErrBufferSize, "chunks must be submitted in index order, below the batch capacity"); return kErrBufferSize; }
+    if (shared_ws_) {
+        if (!d_work) { set_error(kErrNull, "shared-workspace batch: workspace pointer required"); return kErrNull; }
+        sym_ptr_[c] = d_work;
+    }
+    const size_t N = (size_t)d_.padded;
+    auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
+    unsigned *hist = d_hist_ + (size_t)c * 3 * 256;
+    CU_TRY(cudaMemsetAsync(hist, 0, 3 * 256 * sizeof(unsigned), st_));
+    const bool fused = forward_fused_eligible(d_rgb, (int)d_.w, (int)d_.h, (int)d_.f) && (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0 &&
+                       !overlaps(sym_ptr_[c], 3 * N, d_rgb, 3 * (size_t)d_.n_pixels);
+    if (fused) {
+        h_fwd_jobs_[c] = FwdFusedJob{d_rgb, sym_ptr_[c], hist, nullptr};
+        CU_TRY(cudaMemcpyAsync(d_fwd_jobs_ + c, h_fwd_jobs_ + c, sizeof(FwdFusedJob), cudaMemcpyHostToDevice, st_));
+        forward_frontend_fused(last_wavelet, d_fwd_jobs_ + c, 1, false, hist, (int)d_.w, (int)d_.h, last_step, device_sm_count(), st_);
+    } else {
+        forward_frontend(last_wavelet, d_rgb, reinterpret_cast<int16_t *>(d_scratch_), sym_ptr_[c], hist, (int)d_.w, (int)d_.h,
+                         (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, last_step, nullptr, st_);
+    }
+    submitted_ = c + 1;
+    return kOk;
+}
+int Engine::encode_finish(uint32_t n) {
+    if (n != submitted_) { set_error(kErrBufferSize, "collect: chunk count differs from the chunks submitted"); return kErrBufferSize; }
+    last_n = n;
+    CU_TRY(cudaEventRecord(ev_[1], st_));
+    build_tables(d_hist_, (int)n * 3, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[2], st_));
+    int rc = run_rans_encode(n);
+    if (rc) { last_n = 0; return rc; }
+    cudaEventElapsedTime(&timings.ms[0], ev_[0], ev_[1]);   // includes the host copies enqueued between the submits
+    cudaEventElapsedTime(&timings.ms[1], ev_[1], ev_[2]);
+    cudaEventElapsedTime(&timings.ms[2], ev_[2], ev_[3]);
+    return kOk;
+}
+
 int Engine::fetch_enqueue(uint32_t i, Chunk &out, bool &direct) {
     if (i >= last_n) { set_error(kErrBufferSize, "chunk index out of range"); return kErrBufferSize; }
     out.width = d_.w; out.height = d_.h; out.frames = d_.f;

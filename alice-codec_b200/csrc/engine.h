@@ -99,6 +99,11 @@ public:
     // coef_dump: optional device i32 [3][N] for chunk 0 (parity tests).
     int encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const *d_rgb, uint32_t n,
                       int32_t *d_coef_dump, uint8_t *const *d_work = nullptr);
+    // The same encode, one chunk at a time: begin, submit chunk 0, 1, ... (each call enqueues that chunk's front-end on the
+    // stream and returns), finish(n) = tables + all rANS streams + one synchronisation.  d_work as in encode_device.
+    int encode_begin(uint8_t quality, uint8_t wavelet);
+    int encode_submit(uint32_t c, const uint8_t *d_rgb, uint8_t *d_work);
+    int encode_finish(uint32_t n);
     // Fill a Chunk (headers + payload copied to the host) from the last encode_device.
     int fetch_chunk(uint32_t i, Chunk &out);
     // The first n chunks of the last encode_device at once: all payload copies enqueued, one synchronisation.
@@ -118,6 +123,7 @@ public:
     uint8_t last_wavelet = 0;
     int last_step = 1;
     uint32_t last_n = 0;
+    uint32_t submitted_ = 0;
 
 private:
     int run_rans_encode(uint32_t n);

@@ -236,6 +236,14 @@ int alice_codec_batch_decode_device(AliceBatch *b, uint8_t *const *d_rgb_out, ui
 int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, uint32_t n, EncodedChunk **out_chunks);
 int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chunks, uint32_t n,
                                   uint8_t *const *h_rgb_out);
+/* The same encode, one chunk at a time (the reference encodes one chunk per call, src/bin/main.rs:107-145): submit chunk
+ * 0, 1, ... in index order as they become available — each call enqueues the host -> device copy and the front-end of
+ * that chunk and returns at once — then collect(n) runs the tables and all 3n rANS streams and returns the chunks after
+ * ONE synchronisation.  The host never has to hold the whole batch: a (pinned) host buffer may be reused once its copy has
+ * completed, e.g. after alice_codec_batch_sync, which waits for everything enqueued so far. */
+int alice_codec_batch_submit_host(AliceBatch *b, uint32_t i, const uint8_t *h_rgb);
+int alice_codec_batch_collect(AliceBatch *b, uint32_t n, EncodedChunk **out_chunks);
+int alice_codec_batch_sync(AliceBatch *b);
 /* copy chunk i of the last encode_device to the host as an EncodedChunk */
 EncodedChunk *alice_codec_batch_get_chunk(AliceBatch *b, uint32_t i);
 /* CUDA-event durations (ms) of the last encode/decode: [0] front-end kernels (all chunks), [1] table build,

@@ -528,3 +528,31 @@ def check_lossless_set(api, shapes=((16, 6, 4), (21, 9, 3), (128, 8, 6))):
         for c in range(3):
             assert ls.stream(c) == ref["streams"][c], (w, h, f, c)
         ls.close()
+
+
+def check_submit_collect(api, shapes=((48, 20, 8), (96, 4, 64)), n=4):
+    """alice_codec_batch_submit_host / _collect: chunk-at-a-time encode through ONE reused host buffer equals the oracle
+    (plain and shared-workspace batches), and out-of-order submits are refused."""
+    for (w, h, f) in shapes:
+        rgbs = [O.generate(O.G1, w, h, f, O.SEED + i) for i in range(n)]
+        refs = [O.encode(r, w, h, f, 80, 1) for r in rgbs]
+        for shared in (False, True):
+            batch = pkg.ChunkBatch(80, "cdf97", w, h, f, n, stream=0, api=api, shared_workspace=shared)
+            buf = np.empty_like(rgbs[0])
+            for i in range(n):
+                buf[:] = rgbs[i]
+                batch.submit_host(i, buf.ctypes.data)
+                batch.sync()                       # the copy has completed: the buffer may be overwritten
+            chunks = batch.collect(n)
+            assert [c.to_bytes() for c in chunks] == refs, (w, h, f, shared)
+            outs = [np.zeros(r.size, dtype=np.uint8) for r in rgbs]
+            batch.decode_host(chunks, [o.ctypes.data for o in outs])
+            for i in range(n):
+                assert np.array_equal(outs[i], O.decode(refs[i])), (w, h, f, shared, i)
+            batch.submit_host(0, rgbs[0].ctypes.data)
+            try:
+                batch.submit_host(2, rgbs[2].ctypes.data)
+                raise AssertionError("out-of-order submit accepted")
+            except pkg.CodecError as e:
+                assert e.kind == "InvalidBufferSize"
+            batch.close()

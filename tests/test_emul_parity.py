@@ -125,3 +125,7 @@ def test_wavelet_api_fast_path(api):
 
 def test_lossless_set(api):
     parity.check_lossless_set(api)
+
+
+def test_batch_submit_collect(api):
+    parity.check_submit_collect(api)

@@ -347,3 +347,7 @@ def test_fullsize_config4_lossless_1080p64(api):
         s = ls.stream(c)
         assert len(s) == g["stream_lens"][c] and sha(s) == g["sha256_streams"][c], f"rANS stream {c}"
     ls.close()
+
+
+def test_batch_submit_collect(api):
+    parity.check_submit_collect(api)

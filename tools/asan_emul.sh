@@ -6,7 +6,7 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=${TMPDIR:-/tmp}/alice_asan
 mkdir -p "$OUT"
-for f in k_forward k_inverse k_rans k_generic k_rdo k_synth engine capi; do
+for f in k_forward k_fwd_fused k_inv_fused k_inverse k_rans k_generic k_wavelet_i32 k_rdo k_synth engine lossless capi; do
   g++ -O1 -g -std=c++17 -fPIC -fwrapv -DALICE_EMUL -x c++ -Wno-unknown-pragmas -I "$ROOT/tests/emul" \
       -fsanitize=address -fno-omit-frame-pointer -c "$ROOT/alice-codec_b200/csrc/$f.cu" -o "$OUT/$f.o" &
 done
@@ -41,11 +41,14 @@ for shape in [(380, 10, 3), (512, 34, 2), (250, 30, 3), (260, 6, 63), (264, 4, 6
 parity.check_rdo_exact_variance(api, rng, sizes=(1, 31, 1025, 5000))
 parity.check_rdo_octants(api, rng, shapes=((8, 6, 4), (9, 7, 5), (2, 2, 2)))
 parity.check_rans_interleaved(api, rng, sizes=(0, 1, 5, 1024, 4099))
-import os
-os.environ["ALICE_RANS_DEC_SPLIT16"] = "1"
-parity.check_rans_api(api, rng, n=3000)
-parity.check_encode_decode(api, O.G1, 260, 4, 64, 80, 1)
-del os.environ["ALICE_RANS_DEC_SPLIT16"]
+# the fused front-end / back-end kernels, the fast Wavelet2D/3D kernels, the lossless set, the payload arena, submit/collect
+for shape in [(80, 2, 64), (128, 6, 64), (112, 40, 64)]:
+    for wv in (0, 1, 2):
+        parity.check_encode_decode(api, O.G1, *shape, 80, wv)
+parity.check_wavelet_fast_path(api)
+parity.check_lossless_set(api)
+parity.check_payload_arena(api)
+parity.check_submit_collect(api)
 print("ASAN RUN OK")
 PY
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 python "$OUT/run.py"

@@ -387,7 +387,6 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     // the two-kernel path, which finishes reading the RGB before the first symbol is written.
     auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
     bool all_fused = true;
-    if (const char *e = getenv("ALICE_FWD_FUSED")) all_fused = e[0] != '0';   // measurement hook (tools/frontend_time.py), removed once decided
     for (uint32_t c = 0; c < n; c++)
         all_fused = all_fused && forward_fused_eligible(d_rgb[c], (int)d_.w, (int)d_.h, (int)d_.f) &&
                     (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0;
@@ -548,9 +547,8 @@ int Engine::run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_
     const int n_sms = device_sm_count();
     std::vector<char> fused(n, 0);
     bool any = false, uniform = true;
-    const char *hook = getenv("ALICE_INV_FUSED");   // measurement hook (tools/frontend_time.py), removed once decided
     for (uint32_t c = 0; c < n; c++) {
-        fused[c] = !(hook && hook[0] == '0') && inverse_fused_eligible(sym_ptr_[c], d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, hdr[c].steps) &&
+        fused[c] = inverse_fused_eligible(sym_ptr_[c], d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, hdr[c].steps) &&
                    !overlaps(sym_ptr_[c], 3 * N, d_rgb_out[c], 3 * (size_t)d_.n_pixels);
         any = any || fused[c];
         uniform = uniform && fused[c] && hdr[c].wavelet == hdr[0].wavelet && hdr[c].steps[0] == hdr[0].steps[0] &&

@@ -201,15 +201,7 @@ void estimate_stream_bytes(const unsigned *d_hist, const EncSym *d_enc, int n_st
     ALICE_LAUNCH(k_estimate_stream_bytes, dim3(n_streams), dim3(256), 0, st, d_hist, d_enc, n_symbols, d_est);
 }
 
-// ------------------------------------------------------------------------ TWO streams per warp
-// A stream's recurrence runs on ONE lane; the other lanes only help in the short lane-parallel phases.  Round 1 gave every
-// stream a warp of its own, so eight streams per SM (what shared memory and HBM capacity allow) meant two warps per warp
-// scheduler, and the two serial loops cost each other issue slots: 41.9 instead of 55 Msym/s per encode lane, 27.9 instead
-// of 32-36 per decode lane (profiles/r02_switches.md).  Here a warp carries two streams, one per half-warp: lanes 0 and 16
-// run the two recurrences in the SAME instructions (one issue slot serves both), lanes 1-15 / 17-31 are the helpers of
-// their half.  Eight streams per SM are then four warps, one per scheduler.
-// Control flow that contains a __syncwarp or a shuffle is kept warp-uniform (loop conditions go through __any_sync, the
-// work inside is predicated per half), so the halves reconverge at every phase boundary and every sync uses the full mask.
+// --------------------------------------------------------------------------------- encode
 template <int V> struct IntC { static constexpr int value = V; };
 #ifndef ALICE_EMUL
 // opt-in to > 48 KB of dynamic shared memory: a per-device function attribute, set once per device and kernel
@@ -222,6 +214,19 @@ template <class K> static void ensure_dyn_smem(K kernel, int bytes, unsigned lon
     done_mask |= bit;
 }
 #endif
+// Block shape per launch (profiles/r02_switches.md).  A launch lasts as long as its slowest stream, and a stream that
+// shares its warp scheduler with another runs at ~3/4 of its speed alone (the serial loops are bound by the latency of
+// their dependent chains, so the two interleave almost for free: 2 x 0.76 = 1.5x the throughput).
+//   * two to eight streams per SM: single-warp blocks; the hardware spreads them evenly over the four schedulers of an
+//     SM at four and at eight blocks per SM (measured: 54.9 / 32.4 Msym/s per lane at four, 41.9 / 27.9 at eight);
+//   * fewer streams than two per SM: four-warp blocks = one warp per scheduler, so that the blocks of several batches
+//     in flight do not pile up on one scheduler (round 1: encode 2.95-3.7 s -> 2.55-2.9 s with three batches in flight);
+//   * more than eight per SM do not fit the decoder's shared memory at once; four-warp blocks keep the waves aligned.
+// Tried and dropped: two streams per WARP, one per half-warp, lanes 0 and 16 running the two recurrences in the same
+// instructions (profiles/r02_rans_two_streams_per_warp.jsonl).  The halves do execute converged (ncu: 2 threads per
+// instruction), but a stream then runs at 42 / 28.7 Msym/s whatever the load: the per-half table base costs the decoder
+// an address add on its dependent chain (68 instead of 60.6 cycles per symbol), and both kernels lose a fifth of their
+// single-stream speed, which is what a one-chunk call through the reference ABI sees.
 int device_sm_count() {
 #ifdef ALICE_EMUL
     return kNumSMs;
@@ -238,51 +243,47 @@ int device_sm_count() {
     return c;
 #endif
 }
-// Warps per block.  A launch that gives every SM at least one warp uses single-warp blocks (the block scheduler spreads
-// them over the SMs, at most four per SM fit the decoder's shared memory and they land on different schedulers); smaller
-// launches use four-warp blocks = one warp per scheduler of an SM, so that the blocks of several batches in flight do not
-// pile up on one scheduler (measured in round 1: encode 2.95-3.7 s -> 2.55-2.9 s with three batches in flight).
 template <class F> static void launch_lanes(int n_streams, F f) {
-    const int warps = (n_streams + 1) / 2;
-    if (warps >= device_sm_count()) f(IntC<1>());
+    const int sms = device_sm_count();
+    if (n_streams >= 2 * sms && n_streams <= 8 * sms) f(IntC<1>());
     else f(IntC<4>());
 }
 
-// --------------------------------------------------------------------------------- encode
-constexpr int kEncBlock = 256;                  // symbols per half-warp fetch (16 bytes per lane)
+constexpr int kEncBlock = 512;                  // symbols per warp-wide fetch (16 bytes per lane)
 constexpr int kEncRing = 2 * kEncBlock + 64;    // bytes one block can emit (2 per symbol) + the 4 state bytes + slack
 constexpr uint32_t kGrpSmall = 1u, kGrpGeneric = 2u;
-constexpr int kEncSmemPerStream = 256 * 16 + kEncBlock * (16 + 4 + 4 + 1) + 16 * 4 + kEncRing;   // 11 136 bytes
-static_assert(kEncSmemPerStream % 16 == 0, "per-stream shared memory must keep 16-byte alignment");
+
+// Streams per block (LPB): with four warps per block = one per SM sub-partition the streams of concurrent launches
+// (several batches in flight) spread evenly over the warp schedulers instead of piling up single-warp blocks on a
+// few of them (measured: encode 2.95-3.7 s -> 2.55-2.9 s with three batches in flight).  A launch that fills the
+// machine on its own uses single-warp blocks, which measured 6-11 % faster there (decode 3.66 s vs 4.06 s).
+constexpr int kEncSmemPerWarp = 256 * 16 + kEncBlock * (16 + 4 + 4 + 1) + 32 * 4 + kEncRing;   // 18 112 bytes
+static_assert(kEncSmemPerWarp % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
 template <int LPB>
 __global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ enc_all,
               unsigned long long *__restrict__ results, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
-    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, lead = half * 16;
-    const int wslot = blockIdx.x * LPB + (threadIdx.x >> 5);
-    if (2 * wslot >= n_streams) return;              // warp-uniform; the kernel has no block-level barrier
-    const int stream = 2 * wslot + half;
-    const bool live = stream < n_streams;            // the second half of the last warp may have no stream
-    unsigned char *smem = smem_all + (size_t)(2 * (threadIdx.x >> 5) + half) * kEncSmemPerStream;
+    const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kEncSmemPerWarp;
     uint4 *tab = reinterpret_cast<uint4 *>(smem);                                   // EncSym of every symbol
-    // staged per symbol of the block, indexed [b][hl] (symbol b of lane hl's group): conflict-free for the lanes
+    // staged per symbol of the block, indexed [b][lane] (symbol b of lane's group): conflict-free for the lanes
     uint4 *st_a = tab + 256;                                                        // {x_lim, rcp, cmpl, cum}
     uint32_t *st_s = reinterpret_cast<uint32_t *>(st_a + kEncBlock);                // division shift sh | (freq <= 16) << 8
     uint32_t *st_x = st_s + kEncBlock;                                              // state before the step of each symbol
     uint32_t *grp = st_x + kEncBlock;                                               // per group of 16 symbols: kGrpSmall | kGrpGeneric
-    uint8_t *ring = reinterpret_cast<uint8_t *>(grp + 16);                          // emitted bytes of the block, filled from the top down
+    uint8_t *ring = reinterpret_cast<uint8_t *>(grp + 32);                          // emitted bytes of the block, filled from the top down
     uint8_t *st_sym = ring + kEncRing;                                              // the symbols themselves (generic path)
-    const bool leader = hl == 0;
-    if (live) {
+    const int lane = threadIdx.x & 31;
+    const bool lane0 = lane == 0;
+    {
         const uint4 *src = reinterpret_cast<const uint4 *>(enc_all + (size_t)stream * 256);
-        for (int i = hl; i < 256; i += 16) tab[i] = src[i];
+        for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     __syncwarp();
-    RansEncJob job;
-    job.symbols = nullptr; job.n = 0; job.out = nullptr; job.cap = 0;
-    if (live) job = jobs[stream];
+    const RansEncJob job = jobs[stream];
     const uint8_t *sym = job.symbols;
     uint8_t *wp = job.out + job.cap;        // the stream ends at out + cap and grows downwards
     uint32_t x = kRansL;                    // rans.rs:244
@@ -290,75 +291,73 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
     uint32_t status = 0;                    // 1 overflow, 2 zero-frequency symbol
     auto room = [&](uint32_t need) { return (unsigned long long)(wp - job.out) >= need; };
 
-    // generic step, any frequency (rans.rs:269-285 literally); every lane of the half computes the same values
+    // generic step, any frequency (rans.rs:269-285 literally)
     auto step_generic = [&](const uint4 e) {
         if (e.w & kEncZero) { status |= 2u; return; }
         while (x > e.x) {                   // while x >= freq << 19 (limit saturated for freq >= 8192: never)
             --sp;
-            ring[sp] = (uint8_t)x;          // every lane stores the same byte
+            ring[sp] = (uint8_t)x;          // every lane stores the same byte (see the note at the state loop)
             x >>= 8;
         }
         const uint32_t f = kProbScale - e.z;
         const uint32_t q = x / f;
         x = x + (e.w & 0xffffu) + q * e.z;  // (q << 12) + x % f + cum
     };
-    // move ring[sp, kEncRing) to the stream (which grows towards lower addresses) and reset the ring.  Called by the whole
-    // warp at the same points; a half with nothing to move moves nothing.
+    // move ring[sp, kEncRing) to the stream (which grows towards lower addresses) and reset the ring
     auto flush = [&]() {
         __syncwarp();
         const uint32_t n = (uint32_t)kEncRing - sp;
         uint8_t *dst = wp - n;
-        for (uint32_t i = hl; i < n; i += 16) dst[i] = ring[sp + i];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = ring[sp + i];
         wp = dst;
         sp = kEncRing;
         __syncwarp();
     };
 
-    long long i = live ? (long long)job.n : 0;  // symbols [0, i) remain; encode from the back (rans.rs:288-294)
+    long long i = (long long)job.n;  // symbols [0, i) remain; encode from the back (rans.rs:288-294)
     // ragged tail until the read pointer is 16-byte aligned
-    if (live && !room(64)) status |= 1u;
+    if (!room(64)) status |= 1u;
     while (i > 0 && ((reinterpret_cast<uintptr_t>(sym + i)) & 15) != 0 && status == 0) {
         step_generic(tab[__ldg(sym + i - 1)]);
         i--;
     }
     flush();
-    // full 256-symbol blocks: one coalesced 16-byte load per lane
+    // full 512-symbol blocks: one coalesced 16-byte load per lane
     uint4 cur = make_uint4(0, 0, 0, 0);
-    if (i >= kEncBlock) cur = __ldg(reinterpret_cast<const uint4 *>(sym + i - kEncBlock) + hl);
-    for (;;) {
-        bool go = i >= kEncBlock && status == 0;
-        if (go && !room(2 * kEncBlock)) { status |= 1u; go = false; }
-        if (!__any_sync(kFullMask, go)) break;
+    if (i >= kEncBlock) cur = __ldg(reinterpret_cast<const uint4 *>(sym + i - kEncBlock) + lane);
+    while (i >= kEncBlock && status == 0) {
+        if (!room(2 * kEncBlock)) { status |= 1u; break; }
         uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (go && i >= 2 * kEncBlock) nxt = __ldg(reinterpret_cast<const uint4 *>(sym + i - 2 * kEncBlock) + hl);
+        if (i >= 2 * kEncBlock) nxt = __ldg(reinterpret_cast<const uint4 *>(sym + i - 2 * kEncBlock) + lane);
         // ---- all lanes: expand this lane's 16 symbols into ready-to-use table entries
-        if (go) {
+        {
             const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
             uint32_t fl = 0;
 #pragma unroll
             for (int b = 0; b < 16; b++) {
                 const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
                 const uint4 t = tab[sy];
-                st_sym[b * 16 + hl] = (uint8_t)sy;
-                st_a[b * 16 + hl] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_s[b * 16 + hl] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
+                st_sym[b * 32 + lane] = (uint8_t)sy;
+                st_a[b * 32 + lane] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
+                st_s[b * 32 + lane] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
                 fl |= t.w >> 24;
             }
-            grp[hl] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
-                      ((fl & ((kEncWide | kEncZero | kEncOne) >> 24)) ? kGrpGeneric : 0u);
+            grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
+                        ((fl & ((kEncWide | kEncZero | kEncOne) >> 24)) ? kGrpGeneric : 0u);
         }
         __syncwarp();
-        // ---- the two leaders only: the state recurrences, last symbol first.  A leader records the state before each step
-        // in st_x; which bytes that step emitted is recomputed from (state, limit) by the lanes of its half afterwards, so
-        // the serial code has no stream pointer to maintain.  Entries of the next group are loaded into each register slot
-        // as soon as the current group has used it, so the loads issue in the shadow of the dependent arithmetic.
-        if (go && leader) {
+        // ---- lane 0 only: the state recurrence, last symbol first.  It records the state before each step in
+        // st_x; which bytes that step emitted is recomputed from (state, limit) by all lanes afterwards, so the
+        // serial code has no stream pointer to maintain.  (One active lane also makes every 16-byte shared load a
+        // single wavefront.)  Entries of the next group are loaded into each register slot as soon as the
+        // current group has used it, so the loads issue in the shadow of the dependent arithmetic.
+        if (lane0) {
             uint4 ea[16];
             uint32_t es[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 16 + 15]; es[b] = st_s[b * 16 + 15]; }
-            uint32_t g = grp[15];
-            for (int c = 15; c >= 0; c--) {
+            for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + 31]; es[b] = st_s[b * 32 + 31]; }
+            uint32_t g = grp[31];
+            for (int c = 31; c >= 0; c--) {
                 const int cn = c > 0 ? c - 1 : 0;
                 const uint32_t gn = grp[cn];
                 if (g == 0) {
@@ -366,7 +365,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                     // computed and selected at the end, so the comparison is off the critical path.
 #pragma unroll
                     for (int b = 15; b >= 0; b--) {
-                        st_x[b * 16 + c] = x;
+                        st_x[b * 32 + c] = x;
                         const bool k = x > ea[b].x;
                         const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
                         const uint32_t sh = es[b];
@@ -374,14 +373,14 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         // floor(floor(x/f) / 256) == floor((x >> 8) / f)
                         const uint32_t xb = (hi >> (sh + 8u)) * ea[b].z + ((x >> 8) + ea[b].w);
                         x = k ? xb : xa;
-                        ea[b] = st_a[b * 16 + cn];
-                        es[b] = st_s[b * 16 + cn];
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
                     }
                 } else if (!(g & kGrpGeneric)) {
                     // some freq in [2, 16]: up to two renormalisation bytes
 #pragma unroll
                     for (int b = 15; b >= 0; b--) {
-                        st_x[b * 16 + c] = x;
+                        st_x[b * 32 + c] = x;
                         const uint32_t lim = ea[b].x;
                         const uint32_t lim2 = (es[b] & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
                         const uint32_t sh = es[b] & 0xffu;
@@ -390,13 +389,13 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         uint32_t sx = k1 ? 8u : 0u;
                         sx = k2 ? 16u : sx;
                         x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
-                        ea[b] = st_a[b * 16 + cn];
-                        es[b] = st_s[b * 16 + cn];
+                        ea[b] = st_a[b * 32 + cn];
+                        es[b] = st_s[b * 32 + cn];
                     }
                 } else {
                     for (int b = 15; b >= 0; b--) {
-                        const uint4 e = tab[st_sym[b * 16 + c]];
-                        st_x[b * 16 + c] = x;
+                        const uint4 e = tab[st_sym[b * 32 + c]];
+                        st_x[b * 32 + c] = x;
                         if (e.w & kEncZero) { status |= 2u; continue; }
                         while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
                         const uint32_t f = kProbScale - e.z;
@@ -404,68 +403,62 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         x = x + (e.w & 0xffffu) + q * e.z;
                     }
 #pragma unroll
-                    for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 16 + cn]; es[b] = st_s[b * 16 + cn]; }
+                    for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
                 }
                 g = gn;
             }
         }
         __syncwarp();
-        x = __shfl_sync(kFullMask, x, lead);
-        status = __shfl_sync(kFullMask, status, lead);
-        const bool emit = go && status == 0;
-        // ---- all lanes: lane c of a half emits the bytes of its group c.  A step that started in state s with limit L
-        // emitted s & 0xff if s > L and then (s >> 8) & 0xff if (s >> 8) > L (at most two bytes, rans.rs:275-279).
+        x = __shfl_sync(kFullMask, x, 0);
+        status = __shfl_sync(kFullMask, status, 0);
+        if (status) break;
+        // ---- all lanes: lane c emits the bytes of group c.  A step that started in state s with limit L emitted
+        // s & 0xff if s > L and then (s >> 8) & 0xff if (s >> 8) > L (at most two bytes, rans.rs:275-279).
         {
             uint32_t kb1 = 0, kb2 = 0;   // bit b: symbol b of my group emitted a first / second byte
-            if (emit) {
 #pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    const uint32_t sx = st_x[b * 16 + hl], lim = st_a[b * 16 + hl].x;
-                    kb1 |= (sx > lim ? 1u : 0u) << b;
-                    kb2 |= ((sx > lim) && ((sx >> 8) > lim) ? 1u : 0u) << b;
-                }
+            for (int b = 0; b < 16; b++) {
+                const uint32_t sx = st_x[b * 32 + lane], lim = st_a[b * 32 + lane].x;
+                kb1 |= (sx > lim ? 1u : 0u) << b;
+                kb2 |= ((sx > lim) && ((sx >> 8) > lim) ? 1u : 0u) << b;
             }
             const uint32_t mine = (uint32_t)(__popc(kb1) + __popc(kb2));
-            // bytes emitted before mine = those of the groups processed earlier = the lanes above me in my half
+            // bytes emitted before mine = those of the groups processed earlier = lanes above me
             uint32_t incl = mine;
 #pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
+            for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t o = __shfl_down_sync(kFullMask, incl, d);
-                if (hl + d < 16) incl += o;
+                if (lane + d < 32) incl += o;
             }
-            const uint32_t total = __shfl_sync(kFullMask, incl, lead);
-            if (emit) {
-                uint32_t pos = sp - (incl - mine);          // my first byte goes to ring[pos - 1]
+            const uint32_t total = __shfl_sync(kFullMask, incl, 0);
+            uint32_t pos = sp - (incl - mine);          // my first byte goes to ring[pos - 1]
 #pragma unroll
-                for (int b = 15; b >= 0; b--) {
-                    const uint32_t sx = st_x[b * 16 + hl];
-                    if (kb1 & (1u << b)) ring[--pos] = (uint8_t)sx;
-                    if (kb2 & (1u << b)) ring[--pos] = (uint8_t)(sx >> 8);
-                }
-                sp -= total;
+            for (int b = 15; b >= 0; b--) {
+                const uint32_t sx = st_x[b * 32 + lane];
+                if (kb1 & (1u << b)) ring[--pos] = (uint8_t)sx;
+                if (kb2 & (1u << b)) ring[--pos] = (uint8_t)(sx >> 8);
             }
+            sp -= total;
         }
         flush();
-        if (emit) {
-            cur = nxt;
-            i -= kEncBlock;
-        }
+        cur = nxt;
+        i -= kEncBlock;
     }
-    if (live && status == 0 && !room(2 * kEncBlock + 8)) status |= 1u;
+    if (status == 0 && !room(2 * kEncBlock + 8)) status |= 1u;
     while (i > 0 && status == 0) {
         step_generic(tab[__ldg(sym + i - 1)]);
         i--;
     }
     // finish (rans.rs:298-308): 4 state bytes, low byte first, then the whole vector is reversed
-    if (live && status == 0) {
+    if (status == 0) {
         ring[sp - 1] = (uint8_t)x;
         ring[sp - 2] = (uint8_t)(x >> 8);
         ring[sp - 3] = (uint8_t)(x >> 16);
         ring[sp - 4] = (uint8_t)(x >> 24);
         sp -= 4;
+        flush();
     }
-    flush();
-    if (live && leader) {
+    if (lane0) {
         results[2 * stream] = (unsigned long long)((job.out + job.cap) - wp);
         results[2 * stream + 1] = status;
     }
@@ -476,30 +469,38 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
     if (n_streams <= 0) return;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        const int warps = (n_streams + 1) / 2;
+        // a four-warp block asks for more than half an SM's shared memory, so no SM hosts two of them: the encoder
+        // step keeps a warp scheduler ~45 % busy and two streams per scheduler (block stacking under concurrent
+        // launches) measured up to 2x slower; a four-warp decode block (195 KB) is exclusive anyway
+        // (single-warp blocks padded to four per SM measured slightly worse under three concurrent batches:
+        //  encode 2.8-2.95 s, decode 3.8-4.3 s vs 2.5-2.9 s and 4.04 s)
         // (small launches: a four-warp block asks for more than half an SM's shared memory so that the blocks of
-        //  concurrent launches do not stack on one SM)
-        const int smem = LPB == 1 ? 2 * kEncSmemPerStream : std::max(LPB * 2 * kEncSmemPerStream, 116 * 1024);
+        //  concurrent launches do not stack on one SM; machine-filling launches take what they need: 72 KB per block)
+        const int smem = LPB == 1 ? kEncSmemPerWarp
+                                  : (n_streams > 4 * device_sm_count() ? LPB * kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024));
 #ifndef ALICE_EMUL
         static unsigned long long attr_done = 0;
-        ensure_dyn_smem(k_rans_encode<LPB>, std::max(LPB * 2 * kEncSmemPerStream, 116 * 1024), attr_done);
+        ensure_dyn_smem(k_rans_encode<LPB>, std::max(LPB * kEncSmemPerWarp, 116 * 1024), attr_done);
 #endif
         auto k = k_rans_encode<LPB>;
-        ALICE_LAUNCH(k, dim3((warps + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);
+        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);
     });
 }
 
 // --------------------------------------------------------------------------------- decode
-constexpr int kDecBlock = 128;                   // symbols per fast block (one 8-byte store per lane of the half)
+constexpr int kDecBlock = 128;                   // symbols per fast block (one 4-byte store per lane)
 constexpr int kWinPos = 512;                     // byte positions held by the window ring
 constexpr int kWinMirror = 2 * kDecBlock + 16;   // positions mirrored past the end: a block reads linearly
-constexpr int kWinFill = 64;                     // bytes converted per refill (4 per lane of the half)
+constexpr int kWinFill = 128;                    // bytes converted per refill (4 per lane)
 // window entry of position p: {bytes p..p+3, bytes p+4..p+7} as two big-endian words; 8 bytes per position makes
 // the renormalisation shift (8 bits per byte) equal to the address increment.
 // Tables: {freq} and {slot - cum} as two u16 arrays (the two 2-byte loads zero-extend for free, so the dependent
-// chain LDS -> IMAD is that of one 8-byte entry).  26.4 KB per stream: eight streams per SM.
+// chain LDS -> IMAD is that of one 8-byte entry).  26.4 KB per stream: eight streams per SM = two per warp scheduler.
+// Measured (profiles/r02_rans_occupancy.md): one stream per scheduler decodes 33-36 Msym/s, two sharing a scheduler
+// 28.8 Msym/s each (the step is latency bound, so the second stream is almost free); the 8-byte-entry layout of round 1
+// (48.9 KB, four streams per SM, 36.2 Msym/s per lane) gave 145 Msym/s per SM against 173+ for this one.
 constexpr int kDecSmemBytes = kDecLutEntries * 4 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
-static_assert(kDecSmemBytes % 16 == 0, "per-stream shared memory must keep 16-byte alignment");
+static_assert(kDecSmemBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 static_assert(kWinPos >= 2 * kDecBlock + 12 + kWinFill + 16, "a refill must not overwrite unread positions");
 
 struct DecState {
@@ -529,23 +530,21 @@ __global__ void ALICE_LAUNCH_BOUNDS(32 * LPB, 1)
 k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ lut_all,
               const DecAux *__restrict__ aux_all, int n_streams) {
     ALICE_DYN_SMEM(smem_all);
-    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15, lead = half * 16;
-    const int wslot = blockIdx.x * LPB + (threadIdx.x >> 5);
-    if (2 * wslot >= n_streams) return;              // warp-uniform; the kernel has no block-level barrier
-    const int stream = 2 * wslot + half;
-    const bool live = stream < n_streams;            // the second half of the last warp may have no stream
+    const int stream = blockIdx.x * LPB + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;                 // warp-uniform; the kernel has no block-level barrier
     constexpr int kTabBytes = kDecLutEntries * 4;
     constexpr int SH = 1;                            // log2 of the table stride in bytes: slot << SH addresses the tables
-    unsigned char *smem = smem_all + (size_t)(2 * (threadIdx.x >> 5) + half) * kDecSmemBytes;
+    unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kDecSmemBytes;
     uint16_t *f16 = reinterpret_cast<uint16_t *>(smem);                         // slot -> freq ...
     uint16_t *b16 = f16 + kDecLutEntries;                                       // ... and slot -> slot - cum
     uint2 *win = reinterpret_cast<uint2 *>(smem + kTabBytes);                   // position -> next 8 bytes, big-endian
     uint8_t *symt = smem + kTabBytes + (kWinPos + kWinMirror) * 8;              // slot -> symbol
     uint16_t *slots = reinterpret_cast<uint16_t *>(symt + kDecLutEntries);      // slots decoded in this block
-    const bool leader = hl == 0;
-    if (live) {
+    const int lane = threadIdx.x & 31;
+    const bool lane0 = lane == 0;
+    {
         const uint32_t *src = lut_all + (size_t)stream * kDecLutEntries;
-        for (int i = hl; i < kDecLutEntries; i += 16) {
+        for (int i = lane; i < kDecLutEntries; i += 32) {
             const uint32_t p = src[i];
             f16[i] = (uint16_t)(((p >> 8) & 0xfffu) + 1u);
             b16[i] = (uint16_t)(p >> 20);
@@ -553,11 +552,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         }
     }
     __syncwarp();
-    RansDecJob job;
-    job.in = nullptr; job.len = 0; job.symbols = nullptr; job.n = 0;
-    DecAux aux;
-    aux.wide_sym = 0xffffffffu; aux.wide_freq = 0; aux.wide_reachable = 0; aux.reserved = 0;
-    if (live) { job = jobs[stream]; aux = aux_all[stream]; }
+    const RansDecJob job = jobs[stream];
+    const DecAux aux = aux_all[stream];
     DecState s;
     s.in = job.in;
     s.len = job.len;
@@ -581,15 +577,14 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
     unsigned long long i = 0;
     const unsigned long long n = job.n;
 
-    // generic steps for symbols [i, upto), every lane of the half computing the same values; true if the rest was filled
-    auto careful = [&](unsigned long long upto) {
+    auto careful = [&](unsigned long long upto) {   // generic steps for symbols [i, upto); true if the rest was filled
         for (; i < upto; i++) {
             const uint32_t xb = s.x;
             const uint32_t sy = dec_step_generic(s, smem, symt, aux.wide_sym, aux.wide_freq);
-            if (leader) out[i] = (uint8_t)sy;
+            if (lane0) out[i] = (uint8_t)sy;
             if (s.pos >= s.len && s.x == xb) {
                 // exhausted stream and a fixed point of the state map: every further symbol is `sy`
-                for (unsigned long long j = i + 1 + hl; j < n; j += 16) out[j] = (uint8_t)sy;
+                for (unsigned long long j = i + 1 + lane; j < n; j += 32) out[j] = (uint8_t)sy;
                 i = n;
                 return true;
             }
@@ -603,25 +598,22 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         if (peel > n) peel = n;
         careful(peel);
     }
-    for (;;) {
-        const bool more = i < n;
-        if (!__any_sync(kFullMask, more)) break;
-        const bool fast = more && fast_ok && (n - i) >= (unsigned long long)kDecBlock && s.x >= kRansL &&
+    while (i < n) {
+        const bool fast = fast_ok && (n - i) >= (unsigned long long)kDecBlock && s.x >= kRansL &&
                           s.pos + 2ull * kDecBlock <= s.len;
-        if (more && !fast) {
+        if (!fast) {
             unsigned long long upto = i + kDecBlock;
             if (upto > n) upto = n;
-            careful(upto);
+            if (careful(upto)) break;
+            continue;
         }
         // ---- make the window cover offsets [o, o + 2*kDecBlock + 12)
         const unsigned long long o = skew + s.pos;
-        if (fast && (!win_started || o >= filled)) { filled = o & ~(unsigned long long)15; win_started = true; }
-        for (;;) {
-            const bool need = fast && filled < o + 2ull * kDecBlock + 12;
-            if (!__any_sync(kFullMask, need)) break;
+        if (!win_started || o >= filled) { filled = o & ~(unsigned long long)15; win_started = true; }
+        while (filled < o + 2ull * kDecBlock + 12) {
             __syncwarp();
-            if (need) {
-                const unsigned long long base = filled + 4ull * hl;     // this lane converts positions base .. base+3
+            {
+                const unsigned long long base = filled + 4ull * lane;   // this lane converts positions base .. base+3
                 uint32_t d[3];                                          // stream bytes base .. base+11
 #pragma unroll
                 for (int k = 0; k < 3; k++)
@@ -637,16 +629,22 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
                     win[idx] = e;
                     if (idx < (uint32_t)kWinMirror) win[kWinPos + idx] = e;
                 }
-                filled += kWinFill;
             }
+            filled += kWinFill;
             __syncwarp();
         }
-        // ---- kDecBlock symbols, state recurrence only: the two leaders, in the same instructions
+        // ---- kDecBlock symbols, state recurrence only
         uint32_t x = s.x;
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
         const smem_addr_t wa0 = smem_addr_of(win) + 8 * wi0;
         smem_addr_t wa = wa0;                                 // running window address: 8 bytes per stream byte
-        if (fast && leader) {
+        // ---- lane 0 only (one active lane: every shared access is a single wavefront)
+        // (Tried in round 2 and dropped, profiles/r02_rans_decoder_chain_variants.jsonl: reading the table entries of both
+        //  likely next states speculatively -- with and without one renormalisation byte -- so that the comparison only
+        //  selects between loaded entries.  Shared-memory loads return in order, so the select waits for the last of five
+        //  or seven loads per symbol: 22-26 Msym/s per lane branch-free, 16-17 with a branch for the two-byte case,
+        //  against 28-32 for this chain.)
+        if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
             uint32_t x3 = x << SH;                            // the state shifted by SH: its low bits address the table
             for (int g = 0; g < kDecBlock / 16; g++) {
@@ -665,7 +663,7 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
                     uint32_t sa = ka ? 8u : 0u, sa3 = ka ? 8u + SH : (uint32_t)SH;
                     sa = kb ? 16u : sa;
                     sa3 = kb ? 16u + SH : sa3;
-                    x3 = __funnelshift_l(v, x, sa3);          // (renormalised x) << SH, without waiting for it
+                    x3 = __funnelshift_l(v, x, sa3);          // (renormalised x) << 3, without waiting for it
                     x = __funnelshift_l(v, x, sa);
                     v = __funnelshift_l(lo, v, sa);
                     wa += sa;                                 // 8 address bytes per consumed stream byte
@@ -673,26 +671,20 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             }
         }
         __syncwarp();
-        x = __shfl_sync(kFullMask, x, lead);
-        const uint32_t adv = __shfl_sync(kFullMask, (uint32_t)(wa - wa0), lead);
+        x = __shfl_sync(kFullMask, x, 0);
+        wa = wa0 + __shfl_sync(kFullMask, (uint32_t)(wa - wa0), 0);
+        s.x = x;
+        s.pos += (unsigned long long)(wa - wa0) / 8;
         __syncwarp();
-        // ---- all lanes of a fast half: slot -> symbol for 8 symbols each, one 8-byte store per lane
-        if (fast) {
-            s.x = x;
-            s.pos += (unsigned long long)adv / 8;
-            const uint4 sv = *reinterpret_cast<const uint4 *>(slots + 8 * hl);
-            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
-            uint32_t ow[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const uint32_t a = symt[(sw[2 * k] & 0xffffu) >> SH], b2 = symt[sw[2 * k] >> (16 + SH)];
-                const uint32_t c2 = symt[(sw[2 * k + 1] & 0xffffu) >> SH], d2 = symt[sw[2 * k + 1] >> (16 + SH)];
-                ow[k] = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
-            }
-            *reinterpret_cast<uint2 *>(out + i + 8 * hl) = make_uint2(ow[0], ow[1]);
-            i += kDecBlock;
+        // ---- all lanes: slot -> symbol for 4 symbols each, one 4-byte store per lane
+        {
+            const uint2 sv = *reinterpret_cast<const uint2 *>(slots + 4 * lane);
+            const uint32_t a = symt[(sv.x & 0xffffu) >> SH], b2 = symt[sv.x >> (16 + SH)];
+            const uint32_t c2 = symt[(sv.y & 0xffffu) >> SH], d2 = symt[sv.y >> (16 + SH)];
+            *reinterpret_cast<uint32_t *>(out + i + 4 * lane) = a | (b2 << 8) | (c2 << 16) | (d2 << 24);
         }
         __syncwarp();
+        i += kDecBlock;
     }
 }
 
@@ -701,14 +693,13 @@ void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecA
     if (n_streams <= 0) return;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        const int warps = (n_streams + 1) / 2;
-        const int smem = LPB * 2 * kDecSmemBytes;      // four-warp blocks: 211 KB, one per SM = eight streams
+        const int smem = LPB * kDecSmemBytes;      // four-warp blocks: 105.6 KB, two per SM
 #ifndef ALICE_EMUL
         static unsigned long long attr_done = 0;
         ensure_dyn_smem(k_rans_decode<LPB>, smem, attr_done);
 #endif
         auto k = k_rans_decode<LPB>;
-        ALICE_LAUNCH(k, dim3((warps + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
+        ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_dec_lut, d_aux, n_streams);
     });
 }
 

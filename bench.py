@@ -15,9 +15,9 @@ One *step* = one pass of the hot path over a batch of independent chunks per GPU
     encode : RGB -> YCoCg-R -> 3-D lifting -> quantise -> symbols + histograms -> frequency tables -> 3B rANS lanes
     decode : tables -> 3B rANS lanes -> dequantise -> inverse lifting -> RGB
 `value`  = frames/s with the RGB inputs resident in HBM (whole job, all GPUs).  A chunk's symbol planes live in the RGB
-           buffer of the previous chunk and its decode lands there too, so a chunk in flight costs its RGB + its payload
-           budget and a step leaves no input behind: the inputs are regenerated on the device INSIDE the timed region at
-           the start of every step (config.inputs says so).
+           buffer of the previous chunk and its decode lands in its own, so a chunk in flight costs its RGB + its
+           payload and a step leaves no input behind: the inputs are regenerated on the device INSIDE the timed region
+           at the start of every step (config.inputs says so).
 `e2e`    = the same metric through the C-ABI batch calls with HOST buffers (pinned): H2D of every RGB chunk, D2H of
            the .alc payloads, H2D of the payloads again for decode, D2H of every decoded RGB chunk; a few host threads
            each drive their own batch so that one batch's copies run under the other batches' rANS kernels.
@@ -302,7 +302,7 @@ def main():
         seeds = [SEED + rank + i * world for i in range(B)]
     bufs = [torch.empty(rgb_bytes, dtype=torch.uint8, device="cuda") for _ in range(B + 1)]
     rgb_ptrs = [t.data_ptr() for t in bufs[1:]]          # chunk i is generated into bufs[i + 1] ...
-    ws_ptrs = [t.data_ptr() for t in bufs[:B]]           # ... its symbol planes and its decode go to bufs[i]
+    ws_ptrs = [t.data_ptr() for t in bufs[:B]]           # ... its symbol planes go to bufs[i] (consumed input of chunk i - 1) ...
 
     def synth_inputs():
         for i in range(B):
@@ -321,7 +321,7 @@ def main():
             out = sharding.gather_stream(blobs, wl["total_chunks"], rank, world, group=gloo)
             if out is not None:
                 blobs_len[0] = sum(len(b) for b in out)
-        batch.decode_device(ws_ptrs)
+        batch.decode_device(rgb_ptrs)                    # ... and its decode lands back in bufs[i + 1] (descending order)
 
     def barrier():
         if world > 1:
@@ -362,7 +362,7 @@ def main():
     g = _golden(wl["golden"])
     if rank == 0 and g:
         alc = batch.get_chunk(0).to_bytes()
-        bit_exact = (sha(alc) == g["sha256_alc"] and sha(bufs[0].cpu().numpy().tobytes()) == g["sha256_decoded"])
+        bit_exact = (sha(alc) == g["sha256_alc"] and sha(bufs[1].cpu().numpy().tobytes()) == g["sha256_decoded"])
 
     # ---- rooflines, from the library's own CUDA events on the launch stream (averaged over the timed steps)
     peak, peak_src = _peaks()
@@ -392,7 +392,7 @@ def main():
         "frontend": rl("encode front-end: k_fwd_fused (+ k_hist_zero_bin_batch), one launch per chunk", "hbm", alg_bytes, fe_ms,
                        traffic.get("frontend_dram_bytes_per_chunk", 0) * B or None,
                        "6 B/px algorithmic (3 in + 3 out); issue bound: DESIGN.md 4.1"),
-        "backend": rl("decode back-end: k_inv_t + k_inv_yx per chunk", "hbm", alg_bytes, be_ms,
+        "backend": rl("decode back-end: k_inv_fused, one launch per chunk", "hbm", alg_bytes, be_ms,
                       traffic.get("backend_dram_bytes_per_chunk", 0) * B or None, "6 B/px algorithmic"),
         "rans_encode": rl("k_rans_encode (one launch, 3 streams per chunk)", "latency", n_sym + payload_bytes, enc_ms, None, lat_note),
         "rans_decode": rl("k_rans_decode (one launch, 3 streams per chunk)", "latency", n_sym + payload_bytes, dec_ms, None, lat_note),
@@ -425,7 +425,7 @@ def main():
         cpu = cpu_baseline_single(wl)
 
     if rank == 0:
-        launches_per_step = B * (1 + 2 + 2) + 2 + 2 + 2 + B   # synth, fused front-end + zero-bin, back-end x2; tables x2, rANS x2 (+ job uploads are copies)
+        launches_per_step = B * (1 + 2 + 1) + 2 + 2 + 1        # per chunk: synth, k_fwd_fused + zero-bin, k_inv_fused; tables x2, rANS x2, size estimate
         line = {"metric": "1080p encode+decode frames/s" if W == 1920 else "encode+decode frames/s",
                 "value": round(value, 2), "unit": "frames/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
@@ -433,7 +433,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "chunks_per_gpu_per_step": B, "frames_per_step": frames_per_step,
                            "inputs": "G1 tri+hash volumes (SURVEY.md Appendix D), one seed per chunk, regenerated on the device "
-                                     "inside every timed step (a chunk's decode lands in the previous chunk's input buffer)",
+                                     "inside every timed step (a chunk's symbol planes live in the previous chunk's input buffer, "
+                                     "its decode lands in its own)",
                            "l2": "inputs (%.1f GB per step per GPU) are far larger than the 126 MB L2" % (B * rgb_bytes / 1e9),
                            "parallelism": f"chunks sharded over {world} GPU(s), no data-path collective"
                                           + ("; host-side gloo gather of the .alc blobs to rank 0 inside the step" if strong else "")},

@@ -556,3 +556,30 @@ def check_submit_collect(api, shapes=((48, 20, 8), (96, 4, 64)), n=4):
             except pkg.CodecError as e:
                 assert e.kind == "InvalidBufferSize"
             batch.close()
+
+
+def check_shifted_in_place(api, shapes=((20, 12, 6), (96, 4, 64)), n=3):
+    """The memory plan of bench.py: n + 1 RGB-sized buffers; chunk i is read from bufs[i + 1], its symbol planes go to
+    bufs[i] (the consumed input of chunk i - 1) and its decode lands back in bufs[i + 1] (the back-end runs the chunks in
+    descending order).  Both fused kernels run in this plan (no buffer is read and written by the same launch)."""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"        # the emulator treats host memory as device memory
+    for (w, h, f) in shapes:
+        for q, wv in ((80, 1), (90, 0), (75, 2)):
+            rgbs = [O.generate(O.G1, w, h, f, O.SEED + i) for i in range(n)]
+            refs = [O.encode(r, w, h, f, q, wv) for r in rgbs]
+            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=0, api=api, shared_workspace=True)
+            size = max(batch.workspace_bytes(), rgbs[0].size)
+            bufs = [torch.zeros(size, dtype=torch.uint8, device=dev) for _ in range(n + 1)]
+            for i, r in enumerate(rgbs):
+                bufs[i + 1][:r.size] = torch.from_numpy(r).to(dev)
+            rgb_ptrs = [t.data_ptr() for t in bufs[1:]]
+            batch.encode_device(rgb_ptrs, [t.data_ptr() for t in bufs[:n]])
+            for i in range(n):
+                assert batch.get_chunk(i).to_bytes() == refs[i], (w, h, f, q, wv, i)
+            batch.decode_device(rgb_ptrs)
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            for i in range(n):
+                assert np.array_equal(bufs[i + 1][:rgbs[i].size].cpu().numpy(), O.decode(refs[i])), (w, h, f, q, wv, i)
+            batch.close()

@@ -129,3 +129,7 @@ def test_lossless_set(api):
 
 def test_batch_submit_collect(api):
     parity.check_submit_collect(api)
+
+
+def test_shifted_in_place_batch(api):
+    parity.check_shifted_in_place(api)

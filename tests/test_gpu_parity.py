@@ -351,3 +351,7 @@ def test_fullsize_config4_lossless_1080p64(api):
 
 def test_batch_submit_collect(api):
     parity.check_submit_collect(api)
+
+
+def test_shifted_in_place_batch(api):
+    parity.check_shifted_in_place(api)

@@ -517,13 +517,14 @@ class ChunkBatch:
     (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t value (0 = default stream)."""
 
     def __init__(self, quality, wavelet, width, height, frames, n_chunks, stream: int = 0, api: Api | None = None,
-                 shared_workspace: bool = False, payload_bytes_per_chunk: int = 0):
+                 shared_workspace: bool = False, payload_bytes_per_chunk: int = 0, small_smem_kernels: bool = False):
         self._api = api or default_api()
         self.n_chunks = n_chunks
         self.shape = (width, height, frames)
         self.shared_workspace = shared_workspace
         self._h = self._api.lib.alice_codec_batch_create_ex2(int(quality), _wavelet_byte(wavelet), width, height, frames,
-                                                             n_chunks, C.c_void_p(stream), 1 if shared_workspace else 0,
+                                                             n_chunks, C.c_void_p(stream),
+                                                             (1 if shared_workspace else 0) | (2 if small_smem_kernels else 0),
                                                              int(payload_bytes_per_chunk))
         if not self._h:
             self._api._raise()

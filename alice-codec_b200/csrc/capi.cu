@@ -973,6 +973,7 @@ AliceBatch *alice_codec_batch_create_ex2(uint8_t quality, uint8_t wavelet, uint3
     b->eng = new (std::nothrow) Engine(d, n_chunks, cap, (cudaStream_t)cuda_stream, false,
                                        (flags & ALICE_BATCH_SHARED_WORKSPACE) != 0);
     if (!b->eng || !b->eng->ok()) { delete b->eng; delete b; return nullptr; }
+    b->eng->set_prefer_small_smem((flags & ALICE_BATCH_SMALL_SMEM_KERNELS) != 0);
     b->quality = quality;
     b->wavelet = wavelet;
     return b;

@@ -386,7 +386,7 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     // the RGB buffer of any chunk j < i (already consumed); a workspace that overlaps its own chunk's RGB falls back to
     // the two-kernel path, which finishes reading the RGB before the first symbol is written.
     auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
-    bool all_fused = true;
+    bool all_fused = !small_smem_;
     for (uint32_t c = 0; c < n; c++)
         all_fused = all_fused && forward_fused_eligible(d_rgb[c], (int)d_.w, (int)d_.h, (int)d_.f) &&
                     (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0;
@@ -443,7 +443,7 @@ int Engine::encode_submit(uint32_t c, const uint8_t *d_rgb, uint8_t *d_work) {
     auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
     unsigned *hist = d_hist_ + (size_t)c * 3 * 256;
     CU_TRY(cudaMemsetAsync(hist, 0, 3 * 256 * sizeof(unsigned), st_));
-    const bool fused = forward_fused_eligible(d_rgb, (int)d_.w, (int)d_.h, (int)d_.f) && (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0 &&
+    const bool fused = !small_smem_ && forward_fused_eligible(d_rgb, (int)d_.w, (int)d_.h, (int)d_.f) && (reinterpret_cast<uintptr_t>(sym_ptr_[c]) & 3) == 0 &&
                        !overlaps(sym_ptr_[c], 3 * N, d_rgb, 3 * (size_t)d_.n_pixels);
     if (fused) {
         h_fwd_jobs_[c] = FwdFusedJob{d_rgb, sym_ptr_[c], hist, nullptr};
@@ -548,7 +548,7 @@ int Engine::run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_
     std::vector<char> fused(n, 0);
     bool any = false, uniform = true;
     for (uint32_t c = 0; c < n; c++) {
-        fused[c] = inverse_fused_eligible(sym_ptr_[c], d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, hdr[c].steps) &&
+        fused[c] = !small_smem_ && inverse_fused_eligible(sym_ptr_[c], d_rgb_out[c], (int)d_.w, (int)d_.h, (int)d_.f, hdr[c].steps) &&
                    !overlaps(sym_ptr_[c], 3 * N, d_rgb_out[c], 3 * (size_t)d_.n_pixels);
         any = any || fused[c];
         uniform = uniform && fused[c] && hdr[c].wavelet == hdr[0].wavelet && hdr[c].steps[0] == hdr[0].steps[0] &&

@@ -86,6 +86,11 @@ public:
     // chunk's RGB staging buffer (host-pointer calls)
     Engine(const Dims &d, uint32_t cap_chunks, uint64_t payload_cap_per_stream, cudaStream_t user_stream,
            bool own_stream, bool shared_workspace = false);
+    // prefer_small_smem: take the two-kernel front-end / back-end (k_forward.cu / k_inverse.cu: no shared memory to speak
+    // of) instead of the fused kernels (one 106-210 KB block per SM).  For batches that run NEXT TO other batches' rANS
+    // launches: a fused block cannot start on an SM whose shared memory is held by eight resident rANS streams and waits
+    // for a whole rANS launch to end, the small kernels slip in beside them.
+    void set_prefer_small_smem(bool v) { small_smem_ = v; }
     uint64_t workspace_bytes() const { return 3 * d_.padded; }
     bool shared_workspace() const { return shared_ws_; }
     ~Engine();
@@ -141,6 +146,7 @@ private:
     uint8_t *d_symbols_ = nullptr;    // [cap][3][N] (absent in shared-workspace mode)
     std::vector<uint8_t *> sym_ptr_;  // per chunk: where its symbol planes [3][N] live
     bool shared_ws_ = false;
+    bool small_smem_ = false;
     unsigned *d_hist_ = nullptr;      // [cap][3][256]
     EncSym *d_enc_ = nullptr;         // [cap*3][256]
     uint32_t *d_dec_lut_ = nullptr;   // [cap*3][4096]

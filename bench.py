@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="chunks in flight per GPU (0 = sized from free HBM)")
     ap.add_argument("--e2e-threads", type=int, default=6, help="host threads (batches in flight) of the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = --steps)")
+    ap.add_argument("--e2e-fused", action="store_true", help="e2e batches take the fused front-end / back-end kernels (default: the small-shared-memory kernels, which can start beside the other batches' resident rANS streams)")
     ap.add_argument("--host-ring", type=int, default=8, help="distinct pinned host input chunks the e2e leg cycles through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -238,7 +239,13 @@ def main():
     from __graft_entry__ import load_package
     # encoded payloads land in page-locked host buffers that the library pools (include/alice_codec.h); a batch of
     # several hundred chunks needs more than the library's modest default to reuse them step after step
-    os.environ.setdefault("ALICE_CODEC_PINNED_POOL_MB", "49152")
+    try:
+        import psutil
+        host_avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        host_avail = 64 << 30
+    n_local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    os.environ.setdefault("ALICE_CODEC_PINNED_POOL_MB", str(max(1024, min(49152, int(host_avail * 0.5 / n_local) >> 20))))
     pkg = load_package()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -247,6 +254,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libalice_codec has no CPU fallback")
     torch.cuda.set_device(local)
+    try:                                     # run this rank's host threads (and first-touch its pinned buffers) on the CPUs
+        import pynvml as nv                  # next to its GPU: at N = 8 the host side of the copies is the e2e limiter
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local))
+    except Exception:  # noqa: BLE001
+        pass
     gloo = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -488,10 +501,16 @@ def run_e2e(args, wl, pkg, api, B, seeds, local, rank, world, barrier, golden, p
     per_chunk = rgb_bytes + pay_chunk + 3 * (16384 + 256 * 16 + 2048)
     fixed_per_batch = rgb_bytes + 12 * n_px
     Be = max(T, min(B, int((free_b - (3 << 29) - T * fixed_per_batch) // per_chunk)))
+    try:                                                # the encoded chunks of a step live in pinned host memory
+        import psutil
+        Be = max(T, min(Be, int(psutil.virtual_memory().available * 0.5 / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) // max(1, pay_chunk))))
+    except Exception:  # noqa: BLE001
+        pass
     shares = [list(range(t, Be, T)) for t in range(T)]
     streams = [torch.cuda.Stream() for _ in range(T)]
     batches = [pkg.ChunkBatch(wl["q"], wl["wavelet"], W, H, F, len(shares[t]), stream=streams[t].cuda_stream, api=api,
-                              shared_workspace=True, payload_bytes_per_chunk=pay_chunk) for t in range(T)]
+                              shared_workspace=True, payload_bytes_per_chunk=pay_chunk, small_smem_kernels=not args.e2e_fused)
+               for t in range(T)]
     KO = 4
     h_out = [[torch.empty(rgb_bytes, dtype=torch.uint8).pin_memory() for _ in range(KO)] for _ in range(T)]
     payload = [0] * T
@@ -563,6 +582,7 @@ def run_e2e(args, wl, pkg, api, B, seeds, local, rank, world, barrier, golden, p
            "ms_per_step": round(1000 * dt / steps, 1),
            "host_buffers": f"pinned; RGB inputs cycle through {K} distinct chunks, outputs through {KO} buffers per thread",
            "timed_with": "host wall clock around synchronous C-ABI batch calls",
+           "kernels": "fused front-end / back-end" if args.e2e_fused else "two-kernel front-end / back-end (ALICE_BATCH_SMALL_SMEM_KERNELS: they start beside the other batches' resident rANS streams)",
            "decoded_matches_oracle_digest": e2e_ok, "pinned_link_probe": link}
     for bt in batches:
         bt.close()

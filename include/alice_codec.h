@@ -209,7 +209,11 @@ AliceBatch *alice_codec_batch_create(uint8_t quality, uint8_t wavelet, uint32_t 
  * front-end (the fused kernel reads RGB and writes symbols in the same launch).  With host pointers the batch's RGB
  * staging buffers double as the workspaces (chunk i's planes live in the staging buffer of chunk i-1).
  * Saves 3 B/px of device memory per chunk in flight. */
-enum { ALICE_BATCH_SHARED_WORKSPACE = 1 };
+/* ALICE_BATCH_SMALL_SMEM_KERNELS — the batch takes the two-kernel front-end / back-end (next to no shared memory) instead
+ * of the fused kernels (one 106-210 KB block per SM).  For batches that run NEXT TO other batches' rANS launches (several
+ * host threads, one batch each): a fused block cannot start on an SM whose shared memory is held by resident rANS streams
+ * and would wait for a whole rANS launch to end; the small kernels slip in beside them.  Same results. */
+enum { ALICE_BATCH_SHARED_WORKSPACE = 1, ALICE_BATCH_SMALL_SMEM_KERNELS = 2 };
 AliceBatch *alice_codec_batch_create_ex(uint8_t quality, uint8_t wavelet, uint32_t width, uint32_t height,
                                         uint32_t frames, uint32_t n_chunks, void *cuda_stream, uint32_t flags);
 /* payload_bytes_per_chunk: device memory reserved for the encoded payload, per chunk on average (0 = the default, one

@@ -568,7 +568,8 @@ def check_shifted_in_place(api, shapes=((20, 12, 6), (96, 4, 64)), n=3):
         for q, wv in ((80, 1), (90, 0), (75, 2)):
             rgbs = [O.generate(O.G1, w, h, f, O.SEED + i) for i in range(n)]
             refs = [O.encode(r, w, h, f, q, wv) for r in rgbs]
-            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=0, api=api, shared_workspace=True)
+            # (CDF 5/3 also with ALICE_BATCH_SMALL_SMEM_KERNELS: the same plan on the two-kernel paths)
+            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=0, api=api, shared_workspace=True, small_smem_kernels=(wv == 0))
             size = max(batch.workspace_bytes(), rgbs[0].size)
             bufs = [torch.zeros(size, dtype=torch.uint8, device=dev) for _ in range(n + 1)]
             for i, r in enumerate(rgbs):

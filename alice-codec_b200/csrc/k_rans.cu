@@ -471,18 +471,14 @@ void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *
     if (n_streams <= 0) return;
     launch_lanes(n_streams, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        // a four-warp block asks for more than half an SM's shared memory, so no SM hosts two of them: the encoder
-        // step keeps a warp scheduler ~45 % busy and two streams per scheduler (block stacking under concurrent
-        // launches) measured up to 2x slower; a four-warp decode block (195 KB) is exclusive anyway
-        // (single-warp blocks padded to four per SM measured slightly worse under three concurrent batches:
-        //  encode 2.8-2.95 s, decode 3.8-4.3 s vs 2.5-2.9 s and 4.04 s)
-        // (small launches: a four-warp block asks for more than half an SM's shared memory so that the blocks of
-        //  concurrent launches do not stack on one SM; machine-filling launches take what they need: 72 KB per block)
-        const int smem = LPB == 1 ? kEncSmemPerWarp
-                                  : (n_streams > 4 * device_sm_count() ? LPB * kEncSmemPerWarp : std::max(LPB * kEncSmemPerWarp, 116 * 1024));
+        // Four-warp blocks take the shared memory they need (72 KB): up to three per SM, so the blocks of several batches
+        // in flight share SMs with two or three streams per scheduler, like the decoder's (105 KB per four-warp block, two
+        // per SM).  Round 1 padded the block to 116 KB to keep an SM to one block -- per-stream speed over throughput --
+        // which left room for only 148 encoder blocks per GPU and queued the launches of the other batches.
+        const int smem = LPB * kEncSmemPerWarp;
 #ifndef ALICE_EMUL
         static unsigned long long attr_done = 0;
-        ensure_dyn_smem(k_rans_encode<LPB>, std::max(LPB * kEncSmemPerWarp, 116 * 1024), attr_done);
+        ensure_dyn_smem(k_rans_encode<LPB>, LPB * kEncSmemPerWarp, attr_done);
 #endif
         auto k = k_rans_encode<LPB>;
         ALICE_LAUNCH(k, dim3((n_streams + LPB - 1) / LPB), dim3(32 * LPB), smem, st, d_jobs, d_enc, d_results, n_streams);

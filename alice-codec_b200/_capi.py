@@ -104,6 +104,11 @@ SIGNATURES = {
     "alice_codec_batch_submit_host": (cint, [vp, u32, vp]),
     "alice_codec_batch_collect": (cint, [vp, u32, C.POINTER(vp)]),
     "alice_codec_batch_sync": (cint, [vp]),
+    "alice_codec_batch_submit_device": (cint, [vp, u32, vp, vp]),
+    "alice_codec_batch_encode_finish": (cint, [vp, u32]),
+    "alice_codec_batch_decode_begin": (cint, [vp, u32]),
+    "alice_codec_batch_decode_next_device": (cint, [vp, u32, vp]),
+    "alice_codec_batch_decode_end": (cint, [vp]),
     "alice_codec_batch_get_chunk": (vp, [vp, u32]),
     "alice_codec_batch_timings": (cint, [vp, C.POINTER(C.c_float)]),
     "alice_codec_batch_device_bytes": (u64, [vp]),

@@ -577,6 +577,25 @@ class ChunkBatch:
         self._api._chk(self._api.lib.alice_codec_batch_collect(self._h, n, out))
         return [EncodedChunk(C.c_void_p(out[i]), self._api) for i in range(n)]
 
+    def submit_device(self, i, d_rgb_ptr, d_workspace_ptr=None):
+        """streaming encode with device pointers: enqueue the front-end of chunk i (submit 0, 1, ... in order); the RGB
+        buffer may be rewritten by work enqueued on the batch's stream afterwards"""
+        self._api._chk(self._api.lib.alice_codec_batch_submit_device(
+            self._h, i, C.c_void_p(int(d_rgb_ptr)), C.c_void_p(int(d_workspace_ptr)) if d_workspace_ptr else None))
+
+    def encode_finish(self, n):
+        """tables + all 3n rANS streams of the submitted chunks, one synchronisation (results stay on the device)"""
+        self._api._chk(self._api.lib.alice_codec_batch_encode_finish(self._h, n))
+
+    def decode_begin(self, n):
+        self._api._chk(self._api.lib.alice_codec_batch_decode_begin(self._h, n))
+
+    def decode_next_device(self, i, d_rgb_out_ptr):
+        self._api._chk(self._api.lib.alice_codec_batch_decode_next_device(self._h, i, C.c_void_p(int(d_rgb_out_ptr))))
+
+    def decode_end(self):
+        self._api._chk(self._api.lib.alice_codec_batch_decode_end(self._h))
+
     def decode_host(self, chunks, h_rgb_out_ptrs):
         n = len(chunks)
         cks = (C.c_void_p * n)(*[c._h for c in chunks])

@@ -1018,19 +1018,34 @@ int alice_codec_batch_encode_host(AliceBatch *b, const uint8_t *const *h_rgb, ui
     // Shared-workspace batches keep the symbol planes of chunk i in the RGB staging buffer of chunk i - 1 (chunk 0: one
     // spare buffer): the front-end of chunk i runs after that of chunk i - 1 has consumed its RGB, and a workspace that is
     // not the chunk's own RGB lets the fused front-end kernel run (Engine::encode_device).
+    // Batches that own their symbol planes need ONE staging buffer: copy, front-end, next chunk, all in stream order, so a
+    // chunk in flight costs 3 B/px (its symbol planes) + its payload, not 3 B/px more for its RGB.
     const bool shared = e->shared_workspace();
-    b->stage_ptrs.resize(n);
-    b->work_ptrs.resize(n);
-    for (uint32_t i = 0; i < n; i++) {
-        uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
-        if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
-        b->stage_ptrs[i] = s;
-        b->work_ptrs[i] = shared ? e->rgb_stage(i) : nullptr;
-        CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
+    int rc = kOk;
+    if (!shared) {
+        uint8_t *s = e->rgb_stage(0);
+        if (!s) return kErrCuda;
+        rc = e->encode_begin(b->quality, b->wavelet);
+        for (uint32_t i = 0; i < n && !rc; i++) {
+            if (!h_rgb[i]) { set_error(kErrNull, "null chunk pointer"); return kErrNull; }
+            CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
+            rc = e->encode_submit(i, s, nullptr);
+        }
+        if (!rc) rc = e->encode_finish(n);
+        if (rc) return rc;
+    } else {
+        b->stage_ptrs.resize(n);
+        b->work_ptrs.resize(n);
+        for (uint32_t i = 0; i < n; i++) {
+            uint8_t *s = e->rgb_stage(i + 1);
+            if (!s || !e->rgb_stage(i)) return kErrCuda;
+            b->stage_ptrs[i] = s;
+            b->work_ptrs[i] = e->rgb_stage(i);
+            CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb[i], bytes, cudaMemcpyHostToDevice, e->stream()));
+        }
+        rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr, b->work_ptrs.data());
+        if (rc) return rc;
     }
-    int rc = e->encode_device(b->quality, b->wavelet, b->stage_ptrs.data(), n, nullptr,
-                              shared ? b->work_ptrs.data() : nullptr);
-    if (rc) return rc;
     std::vector<Chunk *> cks(n);
     for (uint32_t i = 0; i < n; i++) {
         out_chunks[i] = new (std::nothrow) EncodedChunk();
@@ -1058,10 +1073,44 @@ int alice_codec_batch_submit_host(AliceBatch *b, uint32_t i, const uint8_t *h_rg
         int rc = e->encode_begin(b->quality, b->wavelet);
         if (rc) return rc;
     }
-    uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
+    uint8_t *s = e->rgb_stage(shared ? i + 1 : 0);     // engine-owned symbol planes: one staging buffer for every chunk
     if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
     CU_CHECK_RC(cudaMemcpyAsync(s, h_rgb, bytes, cudaMemcpyHostToDevice, e->stream()));
     return e->encode_submit(i, s, shared ? e->rgb_stage(i) : nullptr);
+}
+// Device-pointer form of submit / collect: chunk i's RGB is already on the device (d_workspace as in
+// alice_codec_batch_encode_device_ws, null for batches that own their symbol planes).  Work is enqueued on the batch's stream
+// and the call returns; d_rgb may be overwritten by work enqueued on that stream afterwards (e.g. the next chunk's producer).
+int alice_codec_batch_submit_device(AliceBatch *b, uint32_t i, const uint8_t *d_rgb, uint8_t *d_workspace) {
+    set_error(0, "");
+    if (!b || !d_rgb) { set_error(kErrNull, "null argument"); return kErrNull; }
+    Engine *e = b->eng;
+    if (i >= e->cap_chunks()) { set_error(kErrBufferSize, "chunk index beyond the batch capacity"); return kErrBufferSize; }
+    if (i == 0) {
+        int rc = e->encode_begin(b->quality, b->wavelet);
+        if (rc) return rc;
+    }
+    return e->encode_submit(i, d_rgb, d_workspace);
+}
+int alice_codec_batch_encode_finish(AliceBatch *b, uint32_t n) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->encode_finish(n);
+}
+int alice_codec_batch_decode_begin(AliceBatch *b, uint32_t n) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->decode_resident_begin(n);
+}
+int alice_codec_batch_decode_next_device(AliceBatch *b, uint32_t i, uint8_t *d_rgb_out) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->decode_resident_next(i, d_rgb_out);
+}
+int alice_codec_batch_decode_end(AliceBatch *b) {
+    set_error(0, "");
+    if (!b) { set_error(kErrNull, "null argument"); return kErrNull; }
+    return b->eng->decode_resident_end();
 }
 int alice_codec_batch_collect(AliceBatch *b, uint32_t n, EncodedChunk **out_chunks) {
     set_error(0, "");
@@ -1096,14 +1145,16 @@ int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chun
     b->stage_ptrs.resize(n);
     b->work_ptrs.resize(n);
     for (uint32_t i = 0; i < n; i++) {
-        if (!chunks[i]) { set_error(kErrNull, "null chunk"); return kErrNull; }
+        if (!chunks[i] || !h_rgb_out[i]) { set_error(kErrNull, "null chunk or output pointer"); return kErrNull; }
         cks[i] = &chunks[i]->c;
-        uint8_t *s = e->rgb_stage(shared ? i + 1 : i);
+        uint8_t *s = e->rgb_stage(shared ? i + 1 : 0);   // engine-owned symbol planes: one staging buffer, see encode_host
         if (!s || (shared && !e->rgb_stage(i))) return kErrCuda;
         b->stage_ptrs[i] = s;
         b->work_ptrs[i] = shared ? e->rgb_stage(i) : nullptr;
     }
-    int rc = e->decode_chunks(cks.data(), n, b->stage_ptrs.data(), shared ? b->work_ptrs.data() : nullptr);
+    if (!shared)     // back-end and device -> host copy chunk by chunk (Engine::decode_chunks synchronises at the end)
+        return e->decode_chunks(cks.data(), n, b->stage_ptrs.data(), nullptr, h_rgb_out);
+    int rc = e->decode_chunks(cks.data(), n, b->stage_ptrs.data(), b->work_ptrs.data());
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++)
         CU_CHECK_RC(cudaMemcpyAsync(h_rgb_out[i], b->stage_ptrs[i], bytes, cudaMemcpyDeviceToHost, e->stream()));

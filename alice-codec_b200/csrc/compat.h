@@ -26,6 +26,12 @@
 
 #define ALICE_HD __host__ __device__ __forceinline__
 #define ALICE_D __device__ __forceinline__
+// hide a value from the optimiser (keeps a multiply by a power of two a multiply: see the rANS decoder)
+#ifdef ALICE_EMUL
+#define ALICE_OPAQUE(v) ((void)0)
+#else
+#define ALICE_OPAQUE(v) asm volatile("" : "+r"(v))
+#endif
 
 // 32-bit shared-memory addresses for the serial rANS loops: a running address in a register and
 // st.shared with an immediate offset keep the compiler from re-deriving the shared window base per store.
@@ -35,6 +41,10 @@ inline smem_addr_t smem_addr_of(void *p) { return (unsigned char *)p; }
 template <int OFF> inline void smem_st_u8(smem_addr_t a, uint32_t v) { a[OFF] = (unsigned char)v; }
 template <int OFF> inline void smem_st_u16(smem_addr_t a, uint32_t v) { *(uint16_t *)(a + OFF) = (uint16_t)v; }
 template <int OFF> inline uint32_t smem_ld_u32(smem_addr_t a) { return *(const uint32_t *)(a + OFF); }
+template <int OFF> inline void smem_st_v2(smem_addr_t a, uint32_t v0, uint32_t v1) { ((uint32_t *)(a + OFF))[0] = v0; ((uint32_t *)(a + OFF))[1] = v1; }
+template <int OFF> inline void smem_st_v4(smem_addr_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    uint32_t *q = (uint32_t *)(a + OFF); q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3;
+}
 #else
 typedef uint32_t smem_addr_t;
 __device__ __forceinline__ smem_addr_t smem_addr_of(void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,6 +58,12 @@ template <int OFF> __device__ __forceinline__ uint32_t smem_ld_u32(smem_addr_t a
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
     return v;
+}
+template <int OFF> __device__ __forceinline__ void smem_st_v2(smem_addr_t a, uint32_t v0, uint32_t v1) {
+    asm volatile("st.shared.v2.u32 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "r"(v0), "r"(v1));
+}
+template <int OFF> __device__ __forceinline__ void smem_st_v4(smem_addr_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
 }
 #endif
 

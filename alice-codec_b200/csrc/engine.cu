@@ -325,7 +325,7 @@ int Engine::run_rans_encode(uint32_t n) {
         if (fits) used += want;
     }
     CU_TRY(cudaMemcpyAsync(d_enc_jobs_, h_enc_jobs_, S * sizeof(RansEncJob), cudaMemcpyHostToDevice, st_));
-    rans_encode(d_enc_jobs_, d_enc_, d_hist_, d_results_, (int)S, st_);
+    rans_encode(d_enc_jobs_, d_enc_, d_hist_, d_results_, (int)S, st_, small_smem_);
     CU_TRY(cudaEventRecord(ev_[3], st_));
     CU_TRY(cudaMemcpyAsync(h_results_, d_results_, S * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
     CU_TRY(cudaMemcpyAsync(h_hist_, d_hist_, (size_t)S * 256 * sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
@@ -377,6 +377,7 @@ int Engine::encode_device(uint8_t quality, uint8_t wavelet, const uint8_t *const
     last_wavelet = wavelet;
     last_step = step;
     last_n = n;
+    resident_decoded_ = 0;
     CU_TRY(cudaMemsetAsync(d_hist_, 0, (size_t)n * 3 * 256 * sizeof(unsigned), st_));
     CU_TRY(cudaEventRecord(ev_[0], st_));
     // Front-end.  64-frame chunks of even height and a width that is a multiple of 16 take the fused kernel
@@ -430,6 +431,7 @@ int Engine::encode_begin(uint8_t quality, uint8_t wavelet) {
     last_step = quality_to_step(quality);
     last_n = 0;
     submitted_ = 0;
+    resident_decoded_ = 0;
     CU_TRY(cudaEventRecord(ev_[0], st_));
     return kOk;
 }
@@ -573,6 +575,66 @@ int Engine::run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_
     return kOk;
 }
 
+// One chunk's back-end on the stream (no synchronisation): the fused kernel when the shape, the header and the buffers allow.
+int Engine::backend_one(uint32_t c, const BackendHeader &hdr, uint8_t *d_rgb_out) {
+    const size_t N = (size_t)d_.padded;
+    auto overlaps = [&](const uint8_t *a, size_t na, const uint8_t *b, size_t nb) { return a < b + nb && b < a + na; };
+    const bool fused = !small_smem_ && inverse_fused_eligible(sym_ptr_[c], d_rgb_out, (int)d_.w, (int)d_.h, (int)d_.f, hdr.steps) &&
+                       !overlaps(sym_ptr_[c], 3 * N, d_rgb_out, 3 * (size_t)d_.n_pixels);
+    if (fused) {
+        h_inv_jobs_[c] = InvFusedJob{sym_ptr_[c], d_rgb_out};
+        CU_TRY(cudaMemcpyAsync(d_inv_jobs_ + c, h_inv_jobs_ + c, sizeof(InvFusedJob), cudaMemcpyHostToDevice, st_));
+        inverse_backend_fused(hdr.wavelet, d_inv_jobs_ + c, 1, (int)d_.w, (int)d_.h, hdr.steps, device_sm_count(), st_);
+    } else {
+        inverse_backend(hdr.wavelet, sym_ptr_[c], reinterpret_cast<int32_t *>(d_scratch_), d_rgb_out, (int)d_.w, (int)d_.h,
+                        (int)d_.f, (int)d_.pw, (int)d_.ph, (int)d_.pf, hdr.steps, st_);
+    }
+    return kOk;
+}
+
+int Engine::decode_resident_begin(uint32_t n) {
+    if (n > last_n) { set_error(kErrBufferSize, "decode_begin: more chunks than the last encode"); return kErrBufferSize; }
+    const size_t N = (size_t)d_.padded;
+    const uint32_t S = n * 3;
+    resident_decoded_ = 0;
+    CU_TRY(cudaEventRecord(ev_[4], st_));
+    build_tables(d_hist_, (int)S, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
+    CU_TRY(cudaEventRecord(ev_[5], st_));
+    for (uint32_t s = 0; s < S; s++) {
+        h_dec_jobs_[s].in = stream_base_[s] + stream_off_[s];
+        h_dec_jobs_[s].len = stream_len_[s];
+        h_dec_jobs_[s].symbols = sym_ptr_[s / 3] + (size_t)(s % 3) * N;
+        h_dec_jobs_[s].n = N;
+    }
+    CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
+    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_, small_smem_);
+    CU_TRY(cudaEventRecord(ev_[6], st_));
+    CU_TRY(cudaGetLastError());
+    resident_decoded_ = n;
+    return kOk;
+}
+
+int Engine::decode_resident_next(uint32_t c, uint8_t *d_rgb_out) {
+    if (c >= resident_decoded_) { set_error(kErrBufferSize, "decode_next: chunk index beyond the last decode_begin"); return kErrBufferSize; }
+    if (!d_rgb_out) { set_error(kErrNull, "null output pointer"); return kErrNull; }
+    int rc = backend_one(c, BackendHeader{last_wavelet, {last_step, last_step, last_step}}, d_rgb_out);
+    if (rc) return rc;
+    CU_TRY(cudaGetLastError());
+    return kOk;
+}
+
+int Engine::decode_resident_end() {
+    CU_TRY(cudaEventRecord(ev_[7], st_));
+    CU_TRY(cudaStreamSynchronize(st_));
+    CU_TRY(cudaGetLastError());
+    if (resident_decoded_) {
+        cudaEventElapsedTime(&timings.ms[3], ev_[4], ev_[5]);
+        cudaEventElapsedTime(&timings.ms[4], ev_[5], ev_[6]);
+        cudaEventElapsedTime(&timings.ms[5], ev_[6], ev_[7]);
+    }
+    return kOk;
+}
+
 int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     if (n > last_n) { set_error(kErrBufferSize, "decode_device: more chunks than the last encode"); return kErrBufferSize; }
     const size_t N = (size_t)d_.padded;
@@ -587,7 +649,7 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
         h_dec_jobs_[s].n = N;
     }
     CU_TRY(cudaMemcpyAsync(d_dec_jobs_, h_dec_jobs_, S * sizeof(RansDecJob), cudaMemcpyHostToDevice, st_));
-    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
+    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_, small_smem_);
     CU_TRY(cudaEventRecord(ev_[6], st_));
     {
         std::vector<BackendHeader> hdr(n);
@@ -604,12 +666,15 @@ int Engine::decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n) {
     return kOk;
 }
 
-int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work) {
+int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work,
+                          uint8_t *const *h_rgb_out) {
     if (n > cap_) { set_error(kErrBufferSize, "batch larger than engine capacity"); return kErrBufferSize; }
+    if (h_rgb_out && shared_ws_) { set_error(kErrDimensions, "interleaved host copies need engine-owned symbol planes"); return kErrDimensions; }
     // This call reuses the histogram, table, payload and overflow buffers of the last encode: whatever encode_device left
     // resident is gone afterwards (fetch_chunk / decode_device_resident then report "out of range" instead of returning
     // another batch's data).
     last_n = 0;
+    resident_decoded_ = 0;
     for (size_t s = 0; s < stream_base_.size(); s++) { stream_base_[s] = nullptr; stream_len_[s] = 0; stream_off_[s] = 0; }
     if (shared_ws_)   // the symbol planes of chunk i live in its workspace, by default its output buffer (>= workspace_bytes())
         for (uint32_t i = 0; i < n; i++) sym_ptr_[i] = d_work ? d_work[i] : d_rgb_out[i];
@@ -677,7 +742,7 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
     CU_TRY(cudaEventRecord(ev_[4], st_));
     build_tables(d_hist_, (int)S, 256, d_enc_, d_dec_lut_, d_aux_, nullptr, nullptr, nullptr, st_);
     CU_TRY(cudaEventRecord(ev_[5], st_));
-    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_);
+    rans_decode(d_dec_jobs_, d_dec_lut_, d_aux_, (int)S, st_, small_smem_);
     CU_TRY(cudaEventRecord(ev_[6], st_));
     {
         std::vector<BackendHeader> hdr(n);
@@ -685,8 +750,18 @@ int Engine::decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const
             const Chunk &ck = *chunks[i];
             hdr[i] = BackendHeader{ck.wavelet, {ck.ch[0].quant_step, ck.ch[1].quant_step, ck.ch[2].quant_step}};
         }
-        int rc = run_backend(n, hdr.data(), d_rgb_out);
-        if (rc) return rc;
+        if (h_rgb_out) {
+            // chunk by chunk: back-end, then the copy to the host, so that every chunk may use the same device buffer
+            const size_t bytes = (size_t)d_.n_pixels * 3;
+            for (uint32_t i = 0; i < n; i++) {
+                int rc = backend_one(i, hdr[i], d_rgb_out[i]);
+                if (rc) return rc;
+                CU_TRY(cudaMemcpyAsync(h_rgb_out[i], d_rgb_out[i], bytes, cudaMemcpyDeviceToHost, st_));
+            }
+        } else {
+            int rc = run_backend(n, hdr.data(), d_rgb_out);
+            if (rc) return rc;
+        }
     }
     CU_TRY(cudaEventRecord(ev_[7], st_));
     CU_TRY(cudaStreamSynchronize(st_));

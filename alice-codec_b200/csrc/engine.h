@@ -115,10 +115,19 @@ public:
     int fetch_chunks(uint32_t n, Chunk *const *out);
     // Decode the payloads the last encode_device left on the device.
     int decode_device_resident(uint8_t *const *d_rgb_out, uint32_t n);
+    // The same decode, one chunk at a time: begin(n) enqueues the tables and all 3n rANS streams, next(c, out) the back-end
+    // of chunk c (any order; nothing synchronises: `out` is valid on the engine's stream after the call, so it may be a
+    // buffer that the caller reuses for a later chunk once its own work on that stream has consumed it).
+    int decode_resident_begin(uint32_t n);
+    int decode_resident_next(uint32_t c, uint8_t *d_rgb_out);
+    int decode_resident_end();        // one synchronisation; fills timings.ms[3..5]
     // Upload n host chunks (headers + payload) and decode them into device buffers d_rgb_out[i].
     // d_work (shared-workspace engines): where chunk i's symbol planes go; default = its output buffer, which keeps the
     // chunk on the two-kernel back-end (see run_backend for the aliasing rules of the fused one)
-    int decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work = nullptr);
+    // h_rgb_out (engine-owned symbol planes only): copy every chunk to host memory right after its back-end, so that
+    // d_rgb_out may name the same device buffer for all chunks
+    int decode_chunks(const Chunk *const *chunks, uint32_t n, uint8_t *const *d_rgb_out, uint8_t *const *d_work = nullptr,
+                      uint8_t *const *h_rgb_out = nullptr);
 
     // staging buffers for host-pointer entry points
     uint8_t *rgb_stage(uint32_t slot);          // device buffer of 3*n_pixels bytes, slot in [0, n_stage)
@@ -134,6 +143,8 @@ private:
     int run_rans_encode(uint32_t n);
     struct BackendHeader { uint8_t wavelet; int steps[3]; };   // what the back-end needs from a chunk's headers
     int run_backend(uint32_t n, const BackendHeader *hdr, uint8_t *const *d_rgb_out);
+    int backend_one(uint32_t c, const BackendHeader &hdr, uint8_t *d_rgb_out);
+    uint32_t resident_decoded_ = 0;   // chunks whose symbol planes decode_resident_begin has queued
     int fetch_enqueue(uint32_t i, Chunk &out, bool &direct);
     Dims d_;
     uint32_t cap_ = 0;

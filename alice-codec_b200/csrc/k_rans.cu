@@ -127,7 +127,8 @@ k_build_tables(const unsigned *__restrict__ hist, int n_symbols, EncSym *__restr
         }
         e.rcp = rcp;
         e.cmpl = kProbScale - f;
-        e.packed = cum | (sh << 16) | (small ? kEncSmall : 0u) | (wide ? kEncWide : 0u) | (zero ? kEncZero : 0u) |
+        // sh in the low five bits (a wrapping shift takes it from there), cum in bits 8..23, flags from bit 24
+        e.packed = sh | (cum << 8) | (small ? kEncSmall : 0u) | (wide ? kEncWide : 0u) | (zero ? kEncZero : 0u) |
                    (one ? kEncOne : 0u);
         enc[(size_t)stream * 256 + tid] = e;
         if (freq_out) freq_out[(size_t)stream * 256 + tid] = (uint16_t)f;
@@ -243,9 +244,9 @@ int device_sm_count() {
     return c;
 #endif
 }
-template <class F> static void launch_lanes(int n_streams, F f) {
+template <class F> static void launch_lanes(int n_streams, bool shared_gpu, F f) {
     const int sms = device_sm_count();
-    if (n_streams >= 2 * sms && n_streams <= 8 * sms) f(IntC<1>());
+    if (!shared_gpu && n_streams >= 2 * sms && n_streams <= 8 * sms) f(IntC<1>());
     else f(IntC<4>());
 }
 
@@ -257,7 +258,7 @@ constexpr uint32_t kGrpSmall = 1u, kGrpGeneric = 2u;
 // (several batches in flight) spread evenly over the warp schedulers instead of piling up single-warp blocks on a
 // few of them (measured: encode 2.95-3.7 s -> 2.55-2.9 s with three batches in flight).  A launch that fills the
 // machine on its own uses single-warp blocks, which measured 6-11 % faster there (decode 3.66 s vs 4.06 s).
-constexpr int kEncSmemPerWarp = 256 * 16 + kEncBlock * (16 + 4 + 4 + 1) + 32 * 4 + kEncRing;   // 18 112 bytes
+constexpr int kEncSmemPerWarp = 256 * 16 + kEncBlock * (16 + 4 + 1) + 32 * 4 + kEncRing;   // 16 064 bytes
 static_assert(kEncSmemPerWarp % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 
 template <int LPB>
@@ -270,9 +271,8 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
     unsigned char *smem = smem_all + (size_t)(threadIdx.x >> 5) * kEncSmemPerWarp;
     uint4 *tab = reinterpret_cast<uint4 *>(smem);                                   // EncSym of every symbol
     // staged per symbol of the block, indexed [b][lane] (symbol b of lane's group): conflict-free for the lanes
-    uint4 *st_a = tab + 256;                                                        // {x_lim, rcp, cmpl, cum}
-    uint32_t *st_s = reinterpret_cast<uint32_t *>(st_a + kEncBlock);                // division shift sh | (freq <= 16) << 8
-    uint32_t *st_x = st_s + kEncBlock;                                              // state before the step of each symbol
+    uint4 *st_a = tab + 256;                                                        // {x_lim, rcp, cmpl, sh | cum << 8 | flags}
+    uint32_t *st_x = reinterpret_cast<uint32_t *>(st_a + kEncBlock);                // state before the step of each symbol
     uint32_t *grp = st_x + kEncBlock;                                               // per group of 16 symbols: kGrpSmall | kGrpGeneric
     uint8_t *ring = reinterpret_cast<uint8_t *>(grp + 32);                          // emitted bytes of the block, filled from the top down
     uint8_t *st_sym = ring + kEncRing;                                              // the symbols themselves (generic path)
@@ -301,7 +301,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
         }
         const uint32_t f = kProbScale - e.z;
         const uint32_t q = x / f;
-        x = x + (e.w & 0xffffu) + q * e.z;  // (q << 12) + x % f + cum
+        x = x + ((e.w >> 8) & 0xffffu) + q * e.z;  // (q << 12) + x % f + cum
     };
     // move ring[sp, kEncRing) to the stream (which grows towards lower addresses) and reset the ring
     auto flush = [&]() {
@@ -338,8 +338,7 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                 const uint32_t sy = (wd[b >> 2] >> (8 * (b & 3))) & 0xff;
                 const uint4 t = tab[sy];
                 st_sym[b * 32 + lane] = (uint8_t)sy;
-                st_a[b * 32 + lane] = make_uint4(t.x, t.y, t.z, t.w & 0xffffu);
-                st_s[b * 32 + lane] = ((t.w >> 16) & 0xffu) | ((t.w & kEncSmall) ? 0x100u : 0u);   // sh | small << 8
+                st_a[b * 32 + lane] = t;
                 fl |= t.w >> 24;
             }
             grp[lane] = ((fl & (kEncSmall >> 24)) ? kGrpSmall : 0u) |
@@ -353,9 +352,8 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
         // current group has used it, so the loads issue in the shadow of the dependent arithmetic.
         if (lane0) {
             uint4 ea[16];
-            uint32_t es[16];
 #pragma unroll
-            for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + 31]; es[b] = st_s[b * 32 + 31]; }
+            for (int b = 0; b < 16; b++) ea[b] = st_a[b * 32 + 31];
             uint32_t g = grp[31];
             for (int c = 31; c >= 0; c--) {
                 const int cn = c > 0 ? c - 1 : 0;
@@ -370,13 +368,13 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         st_x[b * 32 + c] = x;
                         const bool k = x > ea[b].x;
                         const uint32_t hi = __umulhi(x, ea[b].y);       // floor(x / freq) << sh
-                        const uint32_t sh = es[b];
-                        const uint32_t xa = (hi >> sh) * ea[b].z + (x + ea[b].w);
+                        const uint32_t w = ea[b].w;                     // sh | cum << 8 (no flags in this group)
+                        const uint32_t cum = w >> 8;
+                        const uint32_t xa = __funnelshift_r(hi, 0u, w) * ea[b].z + (x + cum);     // the shift wraps: sh = w & 31
                         // floor(floor(x/f) / 256) == floor((x >> 8) / f)
-                        const uint32_t xb = (hi >> (sh + 8u)) * ea[b].z + ((x >> 8) + ea[b].w);
+                        const uint32_t xb = __funnelshift_r(hi, 0u, w + 8u) * ea[b].z + ((x >> 8) + cum);
                         x = k ? xb : xa;
                         ea[b] = st_a[b * 32 + cn];
-                        es[b] = st_s[b * 32 + cn];
                     }
                 } else if (!(g & kGrpGeneric)) {
                     // some freq in [2, 16]: up to two renormalisation bytes
@@ -384,15 +382,15 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                     for (int b = 15; b >= 0; b--) {
                         st_x[b * 32 + c] = x;
                         const uint32_t lim = ea[b].x;
-                        const uint32_t lim2 = (es[b] & 0x100u) ? ((lim << 8) | 0xffu) : 0xffffffffu;
-                        const uint32_t sh = es[b] & 0xffu;
+                        const uint32_t w = ea[b].w;
+                        const uint32_t lim2 = (w & kEncSmall) ? ((lim << 8) | 0xffu) : 0xffffffffu;
+                        const uint32_t sh = w & 31u;
                         const bool k1 = x > lim, k2 = x > lim2;
                         const uint32_t hi = __umulhi(x, ea[b].y);
                         uint32_t sx = k1 ? 8u : 0u;
                         sx = k2 ? 16u : sx;
-                        x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ea[b].w);
+                        x = (hi >> (sh + sx)) * ea[b].z + ((x >> sx) + ((w >> 8) & 0xffffu));
                         ea[b] = st_a[b * 32 + cn];
-                        es[b] = st_s[b * 32 + cn];
                     }
                 } else {
                     for (int b = 15; b >= 0; b--) {
@@ -402,10 +400,10 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
                         while (x > e.x) x >>= 8;       // rans.rs:275-279; the bytes are emitted below
                         const uint32_t f = kProbScale - e.z;
                         const uint32_t q = x / f;
-                        x = x + (e.w & 0xffffu) + q * e.z;
+                        x = x + ((e.w >> 8) & 0xffffu) + q * e.z;
                     }
 #pragma unroll
-                    for (int b = 0; b < 16; b++) { ea[b] = st_a[b * 32 + cn]; es[b] = st_s[b * 32 + cn]; }
+                    for (int b = 0; b < 16; b++) ea[b] = st_a[b * 32 + cn];
                 }
                 g = gn;
             }
@@ -467,11 +465,11 @@ k_rans_encode(const RansEncJob *__restrict__ jobs, const EncSym *__restrict__ en
 }
 
 void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *, unsigned long long *d_results,
-                 int n_streams, cudaStream_t st) {
+                 int n_streams, cudaStream_t st, bool shared_gpu) {
     if (n_streams <= 0) return;
-    launch_lanes(n_streams, [&](auto lpb) {
+    launch_lanes(n_streams, shared_gpu, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
-        // Four-warp blocks take the shared memory they need (72 KB): up to three per SM, so the blocks of several batches
+        // Four-warp blocks take the shared memory they need (63 KB): up to three per SM, so the blocks of several batches
         // in flight share SMs with two or three streams per scheduler, like the decoder's (105 KB per four-warp block, two
         // per SM).  Round 1 padded the block to 116 KB to keep an SM to one block -- per-stream speed over throughput --
         // which left room for only 148 encoder blocks per GPU and queued the launches of the other batches.
@@ -497,6 +495,10 @@ constexpr int kWinFill = 128;                    // bytes converted per refill (
 // Measured (profiles/r02_rans_occupancy.md): one stream per scheduler decodes 33-36 Msym/s, two sharing a scheduler
 // 28.8 Msym/s each (the step is latency bound, so the second stream is almost free); the 8-byte-entry layout of round 1
 // (48.9 KB, four streams per SM, 36.2 Msym/s per lane) gave 145 Msym/s per SM against 173+ for this one.
+// Tried in round 2 and dropped (profiles/r02_rans_twelve_per_sm.md): a 17.7 KB layout (64-symbol blocks, 4-byte window
+// entries, slot -> symbol map read from global memory one block late) that fits TWELVE streams per SM: 270 Msym/s per SM
+// at twelve against 232 here at eight, but 208 at eight and 28.8 instead of 32.4 Msym/s for a stream alone -- and a chunk
+// in flight costs 3 B/px of symbol planes whatever the plan, so HBM holds eight streams per SM of 1080p chunks, not twelve.
 constexpr int kDecSmemBytes = kDecLutEntries * 4 + (kWinPos + kWinMirror) * 8 + kDecLutEntries + kDecBlock * 2;
 static_assert(kDecSmemBytes % 16 == 0, "per-warp shared memory must keep 16-byte alignment");
 static_assert(kWinPos >= 2 * kDecBlock + 12 + kWinFill + 16, "a refill must not overwrite unread positions");
@@ -570,6 +572,16 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
     const unsigned long long end_off = skew + s.len;          // offsets >= end_off are not stream bytes
     unsigned long long filled = 0;                            // window valid for offsets [.., filled)
     bool win_started = false;
+    // the three words a lane converts in a refill starting at offset `at` (whole words may reach past the end of the
+    // stream: the payload arena leaves 16 bytes of slack, Engine::decode_chunks)
+    auto load_words = [&](unsigned long long at, uint32_t (&d)[3]) {
+        const unsigned long long base = at + 4ull * lane;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            d[k] = (base + 4 * k < end_off) ? __ldg(reinterpret_cast<const uint32_t *>(ga + base + 4 * k)) : 0u;
+    };
+    unsigned long long pf_at = ~0ull;                         // offset the prefetched words belong to
+    uint32_t pf_d[3] = {0, 0, 0};
 
     uint8_t *out = job.symbols;
     unsigned long long i = 0;
@@ -613,9 +625,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             {
                 const unsigned long long base = filled + 4ull * lane;   // this lane converts positions base .. base+3
                 uint32_t d[3];                                          // stream bytes base .. base+11
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    d[k] = (base + 4 * k < end_off) ? __ldg(reinterpret_cast<const uint32_t *>(ga + base + 4 * k)) : 0u;
+                if (pf_at == filled) { d[0] = pf_d[0]; d[1] = pf_d[1]; d[2] = pf_d[2]; }   // requested one refill ago
+                else load_words(filled, d);
                 uint32_t be[8];    // be[k] = big-endian word of bytes base+k .. base+k+3
 #pragma unroll
                 for (int k = 0; k < 8; k++)
@@ -631,6 +642,8 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
             filled += kWinFill;
             __syncwarp();
         }
+        // request the bytes of the next refill now: they arrive while lane 0 runs the recurrence
+        if (pf_at != filled) { load_words(filled, pf_d); pf_at = filled; }
         // ---- kDecBlock symbols, state recurrence only
         uint32_t x = s.x;
         const uint32_t wi0 = (uint32_t)(o & (kWinPos - 1));   // window index of the next stream byte
@@ -644,29 +657,32 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
         //  against 28-32 for this chain.)
         if (lane0) {
             uint32_t v = win[wi0].x;                          // the next four stream bytes, big-endian
-            uint32_t x3 = x << SH;                            // the state shifted by SH: its low bits address the table
+            // The loop keeps the state only in its shifted form x3 = x << SH (its low bits address the tables, its high
+            // bits are x >> 12): nine instead of twelve instructions per symbol on the integer pipe, which two streams
+            // on one warp scheduler share (27.9 -> 29.1 Msym/s per lane at eight streams per SM).
+            uint32_t x3 = x << SH;
             for (int g = 0; g < kDecBlock / 16; g++) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) {
                     const uint32_t slot8 = x3 & ((kProbScale - 1) << SH);          // byte offset of the slot's entry
-                    const uint32_t xs = x >> kProbBits;
+                    const uint32_t xs = x3 >> (kProbBits + SH);
                     uint2 e;
                     e.x = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(f16) + slot8);
                     e.y = *reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(b16) + slot8);
                     const uint32_t lo = smem_ld_u32<4>(wa);   // the four bytes after v; address known one symbol early
                     slots[g * 16 + b] = (uint16_t)slot8;
-                    x = e.x * xs + e.y;
-                    // x >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
-                    const bool ka = x < kRansL, kb = x < (1u << 15);
-                    uint32_t sa = ka ? 8u : 0u, sa3 = ka ? 8u + SH : (uint32_t)SH;
-                    sa = kb ? 16u : sa;
+                    const uint32_t xn = e.x * xs + e.y;
+                    // xn >= 2^11 here, so at most two bytes bring it back to [2^23, 2^31)
+                    const bool ka = xn < kRansL, kb = xn < (1u << 15);
+                    uint32_t sa3 = ka ? 8u + SH : (uint32_t)SH;
                     sa3 = kb ? 16u + SH : sa3;
-                    x3 = __funnelshift_l(v, x, sa3);          // (renormalised x) << 3, without waiting for it
-                    x = __funnelshift_l(v, x, sa);
+                    const uint32_t sa = sa3 - SH;
+                    x3 = __funnelshift_l(v, xn, sa3);         // (renormalised x) << SH, without waiting for it
                     v = __funnelshift_l(lo, v, sa);
                     wa += sa;                                 // 8 address bytes per consumed stream byte
                 }
             }
+            x = x3 >> SH;
         }
         __syncwarp();
         x = __shfl_sync(kFullMask, x, 0);
@@ -687,9 +703,9 @@ k_rans_decode(const RansDecJob *__restrict__ jobs, const uint32_t *__restrict__ 
 }
 
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool shared_gpu) {
     if (n_streams <= 0) return;
-    launch_lanes(n_streams, [&](auto lpb) {
+    launch_lanes(n_streams, shared_gpu, [&](auto lpb) {
         constexpr int LPB = decltype(lpb)::value;
         const int smem = LPB * kDecSmemBytes;      // four-warp blocks: 105.6 KB, two per SM
 #ifndef ALICE_EMUL

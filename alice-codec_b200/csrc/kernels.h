@@ -75,8 +75,10 @@ struct RansEncJob {      // device-visible description of one stream to encode
     unsigned long long cap;
 };
 // results[i] = {len, status}: status 0 ok, 1 overflow (cap too small), 2 zero-frequency symbol (reference aborts)
+// shared_gpu: other launches run beside this one (several batches in flight): four-warp blocks = one stream per warp
+// scheduler and block, so the streams of concurrent launches spread evenly over the schedulers
 void rans_encode(const RansEncJob *d_jobs, const EncSym *d_enc, const unsigned *d_hist, unsigned long long *d_results,
-                 int n_streams, cudaStream_t st);
+                 int n_streams, cudaStream_t st, bool shared_gpu = false);
 struct RansDecJob {
     const uint8_t *in;
     unsigned long long len;
@@ -84,7 +86,7 @@ struct RansDecJob {
     unsigned long long n;
 };
 void rans_decode(const RansDecJob *d_jobs, const uint32_t *d_dec_lut, const DecAux *d_aux, int n_streams,
-                 cudaStream_t st);
+                 cudaStream_t st, bool shared_gpu = false);
 
 // ---- generic element-wise / line kernels behind the public stage API (k_generic.cu) -----
 void lift_axis(int32_t *d_data, int32_t *d_tmp, int wavelet, bool inverse, int axis, long long w, long long h,

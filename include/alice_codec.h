@@ -233,7 +233,9 @@ int alice_codec_batch_encode_device(AliceBatch *b, const uint8_t *const *d_rgb, 
 /* decodes what the last encode left on the device into d_rgb_out[i] (tables rebuilt from the histograms) */
 int alice_codec_batch_decode_device(AliceBatch *b, uint8_t *const *d_rgb_out, uint32_t n);
 /* host-buffer variants: host<->device copies are part of the call.  encode_host returns after ONE stream
- * synchronisation for the whole batch (every payload copy is enqueued first).
+ * synchronisation for the whole batch (every payload copy is enqueued first).  A batch that owns its symbol planes (no
+ * ALICE_BATCH_SHARED_WORKSPACE) stages the RGB of all chunks through ONE device buffer, in stream order: a chunk in flight
+ * costs 3 B per padded pixel + its payload of device memory.
  * Call order: alice_codec_batch_decode_host reuses the histogram / table / payload buffers of the batch, so whatever
  * the last encode left resident on the device is gone afterwards: alice_codec_batch_get_chunk and
  * alice_codec_batch_decode_device then fail with ALICE_ERR_BUFFER_SIZE until the next encode. */
@@ -248,6 +250,21 @@ int alice_codec_batch_decode_host(AliceBatch *b, const EncodedChunk *const *chun
 int alice_codec_batch_submit_host(AliceBatch *b, uint32_t i, const uint8_t *h_rgb);
 int alice_codec_batch_collect(AliceBatch *b, uint32_t n, EncodedChunk **out_chunks);
 int alice_codec_batch_sync(AliceBatch *b);
+/* Device-pointer streaming: the same pipeline with the RGB already on the device, for batches whose chunks in flight do not
+ * fit HBM as RGB (a chunk in flight then costs its symbol planes, 3 B per padded pixel, + its payload).
+ *   encode: submit_device(0), (1), ... in index order — each call enqueues that chunk's front-end on the batch's stream and
+ *           returns; d_rgb may be rewritten by work enqueued on that stream afterwards (d_workspace: as in
+ *           alice_codec_batch_encode_device_ws, null for batches that own their symbol planes) — then encode_finish(n) =
+ *           tables + all 3n rANS streams + one synchronisation; alice_codec_batch_get_chunk fetches a result.
+ *   decode: decode_begin(n) enqueues the tables and all 3n rANS streams of what the last encode left resident,
+ *           decode_next_device(i, d_rgb_out) the back-end of chunk i (any order); d_rgb_out is valid on the batch's stream
+ *           after the call, so the caller may hand the same buffer to a later chunk once its own stream-ordered consumer
+ *           has been enqueued; decode_end synchronises. */
+int alice_codec_batch_submit_device(AliceBatch *b, uint32_t i, const uint8_t *d_rgb, uint8_t *d_workspace);
+int alice_codec_batch_encode_finish(AliceBatch *b, uint32_t n);
+int alice_codec_batch_decode_begin(AliceBatch *b, uint32_t n);
+int alice_codec_batch_decode_next_device(AliceBatch *b, uint32_t i, uint8_t *d_rgb_out);
+int alice_codec_batch_decode_end(AliceBatch *b);
 /* copy chunk i of the last encode_device to the host as an EncodedChunk */
 EncodedChunk *alice_codec_batch_get_chunk(AliceBatch *b, uint32_t i);
 /* CUDA-event durations (ms) of the last encode/decode: [0] front-end kernels (all chunks), [1] table build,

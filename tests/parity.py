@@ -584,3 +584,45 @@ def check_shifted_in_place(api, shapes=((20, 12, 6), (96, 4, 64)), n=3):
             for i in range(n):
                 assert np.array_equal(bufs[i + 1][:rgbs[i].size].cpu().numpy(), O.decode(refs[i])), (w, h, f, q, wv, i)
             batch.close()
+
+
+def check_stream_device(api, shapes=((20, 12, 6), (96, 4, 64)), n=4):
+    """Device-pointer streaming (bench.py's memory plan): every chunk's RGB passes through ONE device buffer on the way in
+    (submit_device) and ONE on the way out (decode_next_device); what stays per chunk is its symbol planes and payload.
+    The decoded chunk is copied out on the same stream before the buffer is handed to the next chunk."""
+    import torch
+    cuda = torch.cuda.is_available()
+    dev = "cuda" if cuda else "cpu"                            # the emulator treats host memory as device memory
+    for (w, h, f) in shapes:
+        for q, wv, small in ((80, 1, False), (90, 0, True), (75, 2, False)):
+            rgbs = [O.generate(O.G1, w, h, f, O.SEED + i) for i in range(n)]
+            refs = [O.encode(r, w, h, f, q, wv) for r in rgbs]
+            st = torch.cuda.current_stream().cuda_stream if cuda else 0
+            batch = pkg.ChunkBatch(q, WV[wv], w, h, f, n, stream=st, api=api, small_smem_kernels=small)
+            rot_in = torch.zeros(rgbs[0].size, dtype=torch.uint8, device=dev)
+            rot_out = torch.zeros(rgbs[0].size, dtype=torch.uint8, device=dev)
+            for i, r in enumerate(rgbs):
+                rot_in.copy_(torch.from_numpy(r).to(dev))      # stream-ordered: after the front-end of chunk i - 1
+                batch.submit_device(i, rot_in.data_ptr())
+            try:
+                batch.submit_device(n - 2, rot_in.data_ptr())  # out of order
+                raise AssertionError("out-of-order submit accepted")
+            except pkg.CodecError:
+                pass
+            batch.encode_finish(n)
+            for i in range(n):
+                assert batch.get_chunk(i).to_bytes() == refs[i], (w, h, f, q, wv, i)
+            try:
+                batch.decode_next_device(0, rot_out.data_ptr())     # before decode_begin
+                raise AssertionError("decode_next before decode_begin accepted")
+            except pkg.CodecError:
+                pass
+            batch.decode_begin(n)
+            outs = []
+            for i in (2, 0, 3, 1)[:n]:
+                batch.decode_next_device(i, rot_out.data_ptr())
+                outs.append((i, rot_out.clone()))              # the consumer, on the same stream
+            batch.decode_end()
+            for i, t in outs:
+                assert np.array_equal(t.cpu().numpy(), O.decode(refs[i])), (w, h, f, q, wv, i)
+            batch.close()

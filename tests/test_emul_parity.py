@@ -133,3 +133,7 @@ def test_batch_submit_collect(api):
 
 def test_shifted_in_place_batch(api):
     parity.check_shifted_in_place(api)
+
+
+def test_stream_device_batch(api):
+    parity.check_stream_device(api)

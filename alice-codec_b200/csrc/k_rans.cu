@@ -26,11 +26,11 @@
 // contain a freq in [2, 16] run a two-byte variant; freq == 1, freq > 4096 (the u16-wrapped
 // last symbol of a malformed table) or freq == 0 take a literal step with a true division.
 //
-// Decoder step (src/rans.rs:351-371): {freq, slot - cum} come from a 4096-entry shared table
-// whose address is taken from a second funnel shift ((x << 3) without waiting for x); stream
-// bytes come from a shared "window" table holding, for every byte position, the next eight
-// bytes as two big-endian words (8 bytes per position: the renormalisation shift in bits is
-// the address increment), so renormalisation is two selects and one funnel shift.
+// Decoder step (src/rans.rs:351-371): {freq, slot - cum} come from two 4096-entry u16 shared tables.  The loop keeps
+// the state only as x3 = x << 1: its low bits are the table address, its high bits x >> 12, and the renormalising funnel
+// shift produces the next x3 directly.  Stream bytes come from a shared "window" table holding, for every byte
+// position, the next eight bytes as two big-endian words (8 bytes per position: the renormalisation shift in bits is
+// the address increment), so renormalisation is two selects and two funnel shifts.
 #include <math.h>
 #include <stdlib.h>
 

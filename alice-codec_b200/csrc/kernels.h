@@ -44,7 +44,7 @@ struct EncSym {          // one per symbol, 16 bytes (read as one uint4 {x_lim, 
     uint32_t x_lim;      // renormalise while x > x_lim   (= freq * 2^19 - 1, saturated)
     uint32_t rcp;        // floor(x / freq) == ((x * rcp + rcp) >> 32) >> sh   for x < 2^31 + 2^15
     uint32_t cmpl;       // 4096 - freq  (mod 2^32)
-    uint32_t packed;     // cum (16) | sh << 16 (8) | small(freq <= 16) << 24 | wide(freq > 4096) << 25 | zero << 26
+    uint32_t packed;     // sh (low 5 bits: a wrapping shift reads it in place) | cum << 8 (16) | small(freq <= 16) << 24 | wide(freq > 4096) << 25 | zero << 26 | one << 27
 };
 struct DecAux {          // per stream
     uint32_t wide_sym;   // symbol whose freq is outside [1, 4096] (only the last symbol can be), or 0xffffffff

@@ -49,6 +49,8 @@ parity.check_wavelet_fast_path(api)
 parity.check_lossless_set(api)
 parity.check_payload_arena(api)
 parity.check_submit_collect(api)
+parity.check_stream_device(api)
+parity.check_shifted_in_place(api)
 print("ASAN RUN OK")
 PY
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 python "$OUT/run.py"

@@ -21,9 +21,10 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--decode", action="store_true")
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--lib", default=None, help="experiment build of libalice_codec")
 a = ap.parse_args()
 pkg = load_package()
-api = pkg.default_api()
+api = pkg.Api(a.lib) if a.lib else pkg.default_api()
 api.set_device(0)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize.json")))

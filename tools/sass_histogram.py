@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "alice-codec_b200", "lib", "libalice_codec.so")
+LIB = os.environ.get("ALICE_LIB", os.path.join(ROOT, "alice-codec_b200", "lib", "libalice_codec.so"))
 KERNELS = ["k_fwd_fused<1, false>", "k_fwd_fused<0, false>", "k_inv_fused<1>", "k_inv_fused<0>", "k_rans_encode<1>", "k_rans_encode<4>",
            "k_rans_decode<1>", "k_rans_decode<4>", "k_fwd_xy<1,", "k_fwd_t_quant<1, 4, 64>", "k_inv_t<1, 4, 64, false>", "k_inv_yx<1,",
            "k_wxy<1, false>", "k_wt<1, false>", "k_build_tables", "k_estimate_stream_bytes"]
